@@ -1,0 +1,102 @@
+"""ctypes binding of libconch_b200.so -- the only way the Python side reaches the GPU.
+
+Mirrors include/conch_b200.h one to one.  Loading fails loudly: there is no fallback implementation.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import pathlib
+import threading
+
+_PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libconch_b200.so"
+
+# enums of include/conch_b200.h
+F16, BF16, F32 = 0, 1, 2
+ZP_NONE, ZP_I32, ZP_U8, ZP_ACT = 0, 1, 2, 3
+AUTO, DECODE_MMA, TC_SS, TC_TS, TC2_TS = 0, 1, 2, 3, 4
+VARIANT_NAMES = {AUTO: "auto", DECODE_MMA: "decode_mma", TC_SS: "tc_ss", TC_TS: "tc_ts", TC2_TS: "tc2_ts"}
+ERR_ARG, ERR_SHAPE, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_DEVICE = -1, -2, -3, -4, -5
+WORKSPACE_COUNTER_BYTES = 65536
+
+# every symbol include/conch_b200.h declares (tests check the .so exports exactly these)
+EXPORTS = (
+    "cb200_version",
+    "cb200_last_error",
+    "cb200_mpgemm_workspace_bytes",
+    "cb200_mpgemm",
+    "cb200_last_variant",
+    "cb200_last_launch_count",
+    "cb200_dequantize",
+    "cb200_set_decode_tuning",
+    "cb200_set_tc_tuning",
+)
+
+_lock = threading.Lock()
+_lib: ctypes.CDLL | None = None
+
+
+class LibraryNotBuiltError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the C ABI.  Raises if the library has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise LibraryNotBuiltError(
+                f"{LIB_PATH} is missing. Build it with `python -m conch_b200.build` (needs nvcc). "
+                "conch_b200 has no CPU or Triton fallback."
+            )
+        lib = ctypes.CDLL(str(LIB_PATH))
+        c_void_p, c_int, c_int64, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+        lib.cb200_version.restype = c_int
+        lib.cb200_version.argtypes = []
+        lib.cb200_last_error.restype = ctypes.c_char_p
+        lib.cb200_last_error.argtypes = []
+        lib.cb200_last_variant.restype = c_int
+        lib.cb200_last_variant.argtypes = []
+        lib.cb200_last_launch_count.restype = c_int
+        lib.cb200_last_launch_count.argtypes = []
+        lib.cb200_mpgemm_workspace_bytes.restype = c_size_t
+        lib.cb200_mpgemm_workspace_bytes.argtypes = [c_int64, c_int64, c_int64, c_int, c_int]
+        lib.cb200_mpgemm.restype = c_int
+        lib.cb200_mpgemm.argtypes = [
+            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # x, w_q_packed, w_s, w_zp, out
+            c_int64, c_int64, c_int64,  # M, K, N
+            c_int, c_int, c_int64,  # bits, bias, group_size
+            c_int, c_int, c_int, c_int,  # act_dtype, out_dtype, zp_kind, zp_is_scalar
+            c_void_p, c_size_t,  # workspace
+            c_int, c_void_p,  # variant, stream
+        ]  # fmt: skip
+        lib.cb200_dequantize.restype = c_int
+        lib.cb200_dequantize.argtypes = [
+            c_void_p, c_void_p, c_void_p, c_void_p,
+            c_int64, c_int64,
+            c_int, c_int, c_int64,
+            c_int, c_int, c_int, c_void_p,
+        ]  # fmt: skip
+        lib.cb200_set_decode_tuning.restype = None
+        lib.cb200_set_decode_tuning.argtypes = [c_int, c_int, c_int, c_int]
+        lib.cb200_set_tc_tuning.restype = None
+        lib.cb200_set_tc_tuning.argtypes = [c_int, c_int]
+        _lib = lib
+    return _lib
+
+
+def raise_for_status(rc: int) -> None:
+    """0 -> ok; <0 -> ValueError / NotImplementedError (reference's exception types); >0 -> CUDA RuntimeError."""
+    if rc == 0:
+        return
+    msg = (load().cb200_last_error() or b"").decode(errors="replace")
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc in (ERR_ARG, ERR_SHAPE, ERR_WORKSPACE):
+        raise ValueError(msg)
+    raise RuntimeError(f"libconch_b200 error {rc}: {msg}")

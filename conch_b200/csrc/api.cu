@@ -1,0 +1,192 @@
+// extern "C" entry points of libconch_b200.so (declared in include/conch_b200.h) + regime dispatch.
+// Replaces the reference's launcher + dispatch (conch/kernels/quantization/gemm.py:482-545 and the platform
+// switch in conch/platforms/__init__.py:14-19): there is exactly one backend, sm_100a.
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cb200 {
+
+static thread_local char tls_error[512] = {0};
+static thread_local int tls_last_variant = 0;
+static thread_local int tls_last_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tls_error, sizeof(tls_error), fmt, ap);
+  va_end(ap);
+}
+
+static int check_device() {
+  static std::once_flag once;
+  static int status = 0;
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      status = CB200_ERR_DEVICE;
+      return;
+    }
+    if (prop.major != 10) status = CB200_ERR_DEVICE;
+  });
+  if (status != 0) set_error("libconch_b200 requires an sm_100 (B200) device; there is no fallback path");
+  return status;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int validate(const void* x, const void* wq, const void* ws, const void* wzp, const void* out, int64_t M,
+                    int64_t K, int64_t N, int bits, int64_t* group_size, int act_dtype, int out_dtype, int zp_kind,
+                    bool need_x) {
+  if ((need_x && !x) || !wq || !ws || !out) {
+    set_error("null pointer argument");
+    return CB200_ERR_ARG;
+  }
+  if ((need_x && M <= 0) || K <= 0 || N <= 0) {
+    set_error("non-positive dimension M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
+    return CB200_ERR_ARG;
+  }
+  if (bits != 4 && bits != 8) {
+    set_error("weight_size_bits=%d not supported (4 or 8)", bits);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (act_dtype != CB200_F16 && act_dtype != CB200_BF16) {
+    set_error("activation dtype %d not supported (fp16 or bf16)", act_dtype);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (out_dtype != CB200_F16 && out_dtype != CB200_BF16 && out_dtype != CB200_F32) {
+    set_error("output dtype %d not supported", out_dtype);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (zp_kind < CB200_ZP_NONE || zp_kind > CB200_ZP_ACT || (zp_kind != CB200_ZP_NONE && !wzp)) {
+    set_error("bad zero-point kind %d / pointer", zp_kind);
+    return CB200_ERR_ARG;
+  }
+  if (*group_size == -1) *group_size = K;
+  const int64_t g = *group_size;
+  if (K % 64 != 0 || N % 64 != 0) {
+    set_error("K=%lld and N=%lld must be multiples of 64 (the reference kernel's unmasked 64x64 weight tile)",
+              (long long)K, (long long)N);
+    return CB200_ERR_SHAPE;
+  }
+  if (g <= 0 || g > K || K % g != 0 || (g % 64 != 0)) {
+    set_error("group_size=%lld must divide K=%lld and be a multiple of 64 (or -1 / K for per-channel)",
+              (long long)g, (long long)K);
+    return CB200_ERR_SHAPE;
+  }
+  if (M > (1 << 24) || K > (1 << 24) || N > (1 << 24)) {
+    set_error("dimension too large");
+    return CB200_ERR_SHAPE;
+  }
+  if ((need_x && !aligned16(x)) || !aligned16(wq) || !aligned16(out) || (reinterpret_cast<uintptr_t>(ws) & 7u)) {
+    set_error("x, w_q_packed and out must be 16-byte aligned, w_s 8-byte aligned");
+    return CB200_ERR_ARG;
+  }
+  return 0;
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_version(void) { return CB200_VERSION; }
+const char* cb200_last_error(void) { return tls_error; }
+int cb200_last_variant(void) { return tls_last_variant; }
+int cb200_last_launch_count(void) { return tls_last_launches; }
+
+void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_words) {
+  g_decode_tuning = {warps_n, warps_k, split_k, vec_words};
+}
+void cb200_set_tc_tuning(int m_tile, int split_k) { g_tc_tuning = {m_tile, split_k}; }
+
+size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_size_bits, int variant) {
+  (void)weight_size_bits;
+  (void)variant;
+  const size_t a = decode_workspace_bytes(M, K, N);
+  const size_t b = tc_workspace_bytes(M, K, N);
+  return a > b ? a : b;
+}
+
+int cb200_dequantize(const void* w_q_packed, const void* w_s, const void* w_zp, void* w_out, int64_t K, int64_t N,
+                     int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype, int zp_kind,
+                     int zp_is_scalar, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = validate(nullptr, w_q_packed, w_s, w_zp, w_out, 1, K, N, weight_size_bits, &group_size, act_dtype, act_dtype,
+                zp_kind, false);
+  if (rc) return rc;
+  Problem p{};
+  p.wq = reinterpret_cast<const uint32_t*>(w_q_packed);
+  p.s = w_s;
+  p.zp = w_zp;
+  p.out = w_out;
+  p.M = 0;
+  p.K = int(K);
+  p.N = int(N);
+  p.bias = weight_bias;
+  p.g = int(group_size);
+  p.zp_kind = zp_kind;
+  p.zp_scalar = zp_is_scalar;
+  p.out_dtype = act_dtype;
+  return launch_dequant(p, weight_size_bits, act_dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M,
+                 int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
+                 int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
+                 void* stream) {
+  tls_last_variant = 0;
+  tls_last_launches = 0;
+  int rc = check_device();
+  if (rc) return rc;
+  rc = validate(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, &group_size, act_dtype, out_dtype, zp_kind,
+                true);
+  if (rc) return rc;
+  if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 15u)) {
+    set_error("workspace must be 16-byte aligned");
+    return CB200_ERR_ARG;
+  }
+  Problem p{};
+  p.x = x;
+  p.wq = reinterpret_cast<const uint32_t*>(w_q_packed);
+  p.s = w_s;
+  p.zp = w_zp;
+  p.out = out;
+  p.M = int(M);
+  p.K = int(K);
+  p.N = int(N);
+  p.bias = weight_bias;
+  p.g = int(group_size);
+  p.zp_kind = zp_kind;
+  p.zp_scalar = zp_is_scalar;
+  p.out_dtype = out_dtype;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  int chosen = variant;
+  if (chosen == CB200_AUTO) {
+    // regime split: HBM-bound skinny GEMM up to 16 rows, tensor-core pipeline above
+    chosen = (M <= 16 || !tc_supported(p, weight_size_bits)) ? CB200_DECODE_MMA : CB200_TC_SS;
+  }
+  int launches = 0;
+  if (chosen == CB200_DECODE_MMA) {
+    rc = launch_decode(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
+  } else if (chosen == CB200_TC_SS || chosen == CB200_TC_TS || chosen == CB200_TC2_TS) {
+    if (!tc_supported(p, weight_size_bits)) {
+      set_error("tcgen05 variant %d does not support this problem", chosen);
+      return CB200_ERR_UNSUPPORTED;
+    }
+    rc = launch_tc(p, weight_size_bits, act_dtype, chosen, workspace, workspace_bytes, st, &launches);
+  } else {
+    set_error("unknown variant %d", variant);
+    return CB200_ERR_ARG;
+  }
+  tls_last_variant = chosen;
+  tls_last_launches = launches;
+  return rc;
+}
+
+}  // extern "C"

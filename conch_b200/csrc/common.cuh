@@ -1,0 +1,88 @@
+// Shared host/device plumbing for libconch_b200: problem descriptor, error reporting, small PTX wrappers.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/conch_b200.h"
+
+namespace cb200 {
+
+// One mixed-precision GEMM problem, as the kernels see it (all device pointers).
+struct Problem {
+  const void* x;       // [M, K] act
+  const uint32_t* wq;  // [K/pf, N] packed
+  const void* s;       // [K/g, N] act
+  const void* zp;      // [K/g, N] / [1] / null
+  void* out;           // [M, N]
+  int M, K, N;
+  int bias;         // weight_bias
+  int g;            // group size in k (already resolved: -1 -> K)
+  int zp_kind;      // cb200_zp_kind
+  int zp_scalar;    // w_zp.numel() == 1
+  int out_dtype;    // cb200_dtype
+};
+
+void set_error(const char* fmt, ...);
+
+#define CB200_CUDA_CHECK(expr)                                                        \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::cb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return static_cast<int>(_e);                                                    \
+    }                                                                                 \
+  } while (0)
+
+// ---- launchers implemented in the per-kernel translation units ----------------------------------------
+int launch_dequant(const Problem& p, int bits, int act_dtype, cudaStream_t stream);
+int launch_decode(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream,
+                  int* launches);
+size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N);
+int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, size_t ws_bytes,
+              cudaStream_t stream, int* launches);
+size_t tc_workspace_bytes(int64_t M, int64_t K, int64_t N);
+bool tc_supported(const Problem& p, int bits);
+
+struct DecodeTuning {
+  int warps_n, warps_k, split_k, vec_words;
+};
+extern DecodeTuning g_decode_tuning;
+struct TcTuning {
+  int m_tile, split_k;
+};
+extern TcTuning g_tc_tuning;
+
+// ---- device helpers -----------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void store_out(void* out, int out_dtype, size_t idx, float v) {
+  if (out_dtype == CB200_F16) {
+    reinterpret_cast<__half*>(out)[idx] = __float2half_rn(v);
+  } else if (out_dtype == CB200_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
+  } else {
+    reinterpret_cast<float*>(out)[idx] = v;
+  }
+}
+
+// streaming (read-once) global loads: bypass L1 allocation
+__device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
+               : "=r"(r.x), "=r"(r.y)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace cb200

@@ -1,0 +1,163 @@
+"""Launcher layer: the B200 counterpart of the reference's `conch/kernels/quantization/gemm.py`.
+
+The reference launcher (`mixed_precision_gemm_launcher`, conch/kernels/quantization/gemm.py:482-545) computes a
+Triton grid and JIT-launches `_gemm_kernel`.  Here the launcher marshals raw device pointers into the C ABI
+(`cb200_mpgemm`, include/conch_b200.h) which picks the decode or tcgen05 kernel.  Like the reference launcher
+it does not allocate the output; the only memory it owns is a cached split-K workspace per (device, stream).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from enum import Enum
+
+import torch
+
+from conch_b200 import _lib
+
+
+class WeightGroupMode(Enum):
+    """Dequantisation modes (names follow the reference enum, conch/kernels/quantization/gemm.py:34-41).
+
+    Only the two modes reachable from `mixed_precision_gemm` exist here (conch/ops/quantization/gemm.py:34-38).
+    """
+
+    SYMMETRIC_NO_SHIFT = 2  # W = q * s            (w_zp is None)
+    SYMMETRIC_WITH_SHIFT = 3  # W = (q - zp) * s
+
+
+class ChannelScaleMode(Enum):
+    """conch/kernels/quantization/gemm.py:68-74; the mixed-precision frontend always uses NONE."""
+
+    NONE = 0
+
+
+@dataclass
+class MixedPrecisionMatmulMetadata:
+    """Same 16 fields as the reference dataclass (conch/kernels/quantization/gemm.py:460-479)."""
+
+    m_dim: int
+    k_dim: int
+    n_dim: int
+    weight_size_bits: int
+    weight_bias: int
+    group_size: int
+    elements_per_sample: int
+    zero_is_scalar: bool
+    unpack_mask: int
+    data_contiguous: bool
+    input_dtype: torch.dtype
+    output_dtype: torch.dtype
+    acc_dtype: torch.dtype
+    meta_dtype: torch.dtype
+    channel_scale_mode: ChannelScaleMode
+    weight_group_mode: WeightGroupMode
+
+
+_DTYPE_CODE = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+
+# (device index, stream handle) -> uint8 workspace tensor whose counter prefix is zero between launches
+_workspaces: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, stream: int, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        # must start zeroed: the first WORKSPACE_COUNTER_BYTES bytes are arrival counters that kernels
+        # reset themselves, so this memset happens once per growth, never per call
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def zero_point_kind(x: torch.Tensor, w_zp: torch.Tensor | None) -> int:
+    if w_zp is None:
+        return _lib.ZP_NONE
+    if w_zp.dtype == torch.int32:
+        return _lib.ZP_I32
+    if w_zp.dtype == torch.uint8:
+        return _lib.ZP_U8
+    if w_zp.dtype == x.dtype:
+        return _lib.ZP_ACT
+    raise NotImplementedError(f"w_zp dtype {w_zp.dtype} not supported (int32, uint8 or the dtype of x)")
+
+
+def mixed_precision_gemm_launcher(
+    output: torch.Tensor,
+    x: torch.Tensor,
+    w_q_packed: torch.Tensor,
+    w_s: torch.Tensor,
+    w_zp: torch.Tensor | None,
+    metadata: MixedPrecisionMatmulMetadata,
+    *,
+    variant: int = _lib.AUTO,
+) -> None:
+    """Enqueue out = x @ dequant(W) on the current CUDA stream.  Never synchronises.
+
+    Counterpart of the reference launcher (conch/kernels/quantization/gemm.py:482-545): same argument order.
+    """
+    lib = _lib.load()
+    device = x.device
+    stream = torch.cuda.current_stream(device).cuda_stream
+    m, k, n = metadata.m_dim, metadata.k_dim, metadata.n_dim
+    need = lib.cb200_mpgemm_workspace_bytes(m, k, n, metadata.weight_size_bits, variant)
+    ws = _workspace(device, stream, need)
+    zp_kind = zero_point_kind(x, w_zp)
+    args = (
+        x.data_ptr(),
+        w_q_packed.data_ptr(),
+        w_s.data_ptr(),
+        w_zp.data_ptr() if w_zp is not None else None,
+        output.data_ptr(),
+        m, k, n,
+        metadata.weight_size_bits,
+        metadata.weight_bias,
+        metadata.group_size,
+        _DTYPE_CODE[metadata.input_dtype],
+        _DTYPE_CODE[metadata.output_dtype],
+        zp_kind,
+        int(metadata.zero_is_scalar),
+        ws.data_ptr(),
+        ws.numel(),
+        variant,
+        stream,
+    )  # fmt: skip
+    if device.index is not None and device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):
+            rc = lib.cb200_mpgemm(*args)
+    else:
+        rc = lib.cb200_mpgemm(*args)
+    _lib.raise_for_status(rc)
+
+
+def dequantize_launcher(
+    output: torch.Tensor,
+    w_q_packed: torch.Tensor,
+    w_s: torch.Tensor,
+    w_zp: torch.Tensor | None,
+    weight_size_bits: int,
+    weight_bias: int,
+    group_size: int,
+) -> None:
+    """Enqueue W = dequant(w_q_packed, w_s, w_zp): the reference's `_dequantize` stage on its own
+    (conch/kernels/quantization/gemm.py:176-216)."""
+    lib = _lib.load()
+    device = w_q_packed.device
+    stream = torch.cuda.current_stream(device).cuda_stream
+    k, n = output.shape
+    zp_kind = zero_point_kind(output, w_zp)
+    with torch.cuda.device(device):
+        rc = lib.cb200_dequantize(
+            w_q_packed.data_ptr(),
+            w_s.data_ptr(),
+            w_zp.data_ptr() if w_zp is not None else None,
+            output.data_ptr(),
+            k, n,
+            weight_size_bits, weight_bias, group_size,
+            _DTYPE_CODE[output.dtype],
+            zp_kind,
+            int(w_zp is not None and w_zp.numel() == 1),
+            stream,
+        )  # fmt: skip
+    _lib.raise_for_status(rc)

@@ -1,0 +1,213 @@
+"""Public op: `mixed_precision_gemm` with the reference's exact Python signature.
+
+Drop-in for `conch.ops.quantization.gemm.mixed_precision_gemm` (reference conch/ops/quantization/gemm.py:133-168):
+same positional order, keyword names and defaults, same packing layout (conch/third_party/vllm/quant_utils.py:104-125),
+same group_size semantics, same exception types in strict mode.  Differences, all supersets:
+  * `group_size=-1` is accepted as an alias of K (the reference op would read out of bounds);
+  * shapes / dtypes are always validated (cheaply) -- the reference only checks when `strict=True`;
+  * `w_zp` may be int32 (reference quantiser), uint8 (what vLLM passes) or the activation dtype;
+  * the output is allocated with `torch.empty` (the reference memsets with `torch.zeros`, gemm.py:164).
+There is no CPU / Triton fallback: inputs must live on a B200.
+"""
+
+from __future__ import annotations
+
+from typing import Final
+
+import torch
+
+from conch_b200 import _lib
+from conch_b200.kernels.quantization.gemm import (
+    ChannelScaleMode,
+    MixedPrecisionMatmulMetadata,
+    WeightGroupMode,
+    dequantize_launcher,
+    mixed_precision_gemm_launcher,
+)
+from conch_b200.platform import current_platform
+
+_ACT_DTYPES: Final = (torch.float16, torch.bfloat16)
+_OUT_DTYPES: Final = (torch.float16, torch.bfloat16, torch.float32)
+
+
+def _check_contiguous(x: torch.Tensor, w_q_packed: torch.Tensor, w_s: torch.Tensor, w_zp: torch.Tensor | None) -> bool:
+    return (
+        x.is_contiguous()
+        and w_q_packed.is_contiguous()
+        and w_s.is_contiguous()
+        and (w_zp is None or w_zp.is_contiguous())
+    )
+
+
+def _deduce_weight_group_mode(w_zp: torch.Tensor | None) -> WeightGroupMode:
+    # reference conch/ops/quantization/gemm.py:34-38
+    return WeightGroupMode.SYMMETRIC_NO_SHIFT if w_zp is None else WeightGroupMode.SYMMETRIC_WITH_SHIFT
+
+
+def create_mixed_precision_metadata(
+    x: torch.Tensor,
+    w_q_packed: torch.Tensor,
+    w_s: torch.Tensor,
+    w_zp: torch.Tensor | None,
+    weight_size_bits: int,
+    weight_bias: int,
+    group_size: int,
+    *,
+    output_dtype: torch.dtype | None = None,
+    acc_dtype: torch.dtype | None = None,
+    meta_dtype: torch.dtype | None = None,
+    scaled_activations: bool = False,
+    strict: bool = False,
+) -> MixedPrecisionMatmulMetadata:
+    """Verify sizes / dtypes and deduce metadata (reference conch/ops/quantization/gemm.py:41-130)."""
+    expected_rank: Final = 2
+    for name, t in (("x", x), ("w_q_packed", w_q_packed), ("w_s", w_s), ("w_zp", w_zp)):
+        if t is None or (name == "w_zp" and not strict and t.numel() == 1):
+            continue  # a scalar zero-point may have any rank unless strict (reference :71-73 checks rank only)
+        if t.dim() != expected_rank:
+            raise ValueError(f"Unexpected number of dimensions of input tensor {name}: {t.dim()}")
+    if w_q_packed.dtype not in (torch.int32, torch.uint32):
+        raise ValueError(f"Invalid datatype for packed weights: {w_q_packed.dtype}")
+    if weight_size_bits not in (4, 8):
+        raise NotImplementedError(f"weight_size_bits={weight_size_bits}: only 4 and 8 bit weights are implemented")
+    if x.dtype not in _ACT_DTYPES:
+        raise NotImplementedError(f"activation dtype {x.dtype}: only float16 / bfloat16 are implemented")
+
+    elements_per_sample = 32 // weight_size_bits  # :83-84
+    m_dim, k_dim = x.shape  # :86-87
+    packed_rows, n_dim = w_q_packed.shape
+    if group_size == -1:
+        group_size = k_dim
+    if packed_rows * elements_per_sample != k_dim:
+        raise ValueError(
+            f"w_q_packed has {packed_rows} rows of {elements_per_sample} values, x has K={k_dim} columns"
+        )
+    unpack_mask = 2**weight_size_bits - 1  # :89
+    zero_is_scalar = False if w_zp is None else w_zp.numel() == 1  # :92
+
+    if group_size <= 0 or k_dim % group_size:
+        raise ValueError(f"group_size={group_size} must divide K={k_dim}")
+    expected_meta_shape: Final = (k_dim // group_size, n_dim)  # :96,101
+    if tuple(w_s.shape) != expected_meta_shape:
+        raise ValueError(f"Invalid w_s shape (expected: {expected_meta_shape}, actual: {tuple(w_s.shape)})")
+    if w_zp is not None and not zero_is_scalar and tuple(w_zp.shape) != expected_meta_shape:
+        raise ValueError(f"Invalid w_zp shape (expected: {expected_meta_shape}, actual: {tuple(w_zp.shape)})")
+    if strict and scaled_activations:  # :108-111 (ignored when not strict, like the reference)
+        raise NotImplementedError("Scaled activations not yet implemented (need to deduce correct channel_scale_mode)")
+
+    if w_s.dtype != x.dtype:
+        raise NotImplementedError(f"w_s dtype {w_s.dtype} must equal the activation dtype {x.dtype}")
+    out_dt = x.dtype if output_dtype is None else output_dtype
+    if out_dt not in _OUT_DTYPES:
+        raise NotImplementedError(f"output_dtype {out_dt} not implemented")
+    acc_dt = torch.float32 if acc_dtype is None else acc_dtype
+    if acc_dt != torch.float32:
+        raise NotImplementedError("only float32 accumulation is implemented (the reference default)")
+    meta_dt = x.dtype if meta_dtype is None else meta_dtype
+    if meta_dt != x.dtype:
+        raise NotImplementedError("meta_dtype must equal the activation dtype (the reference default)")
+
+    return MixedPrecisionMatmulMetadata(
+        m_dim=m_dim,
+        k_dim=k_dim,
+        n_dim=n_dim,
+        weight_size_bits=weight_size_bits,
+        weight_bias=weight_bias,
+        group_size=group_size,
+        elements_per_sample=elements_per_sample,
+        zero_is_scalar=zero_is_scalar,
+        unpack_mask=unpack_mask,
+        data_contiguous=_check_contiguous(x, w_q_packed, w_s, w_zp),
+        input_dtype=x.dtype,
+        output_dtype=out_dt,
+        acc_dtype=acc_dt,
+        meta_dtype=meta_dt,
+        channel_scale_mode=ChannelScaleMode.NONE,
+        weight_group_mode=_deduce_weight_group_mode(w_zp),
+    )
+
+
+def _require_device(*tensors: torch.Tensor | None) -> None:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "conch_b200.mixed_precision_gemm needs CUDA tensors on a B200: there is no CPU fallback "
+                f"(got a tensor on {t.device})"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"all tensors must be on the same device ({dev} vs {t.device})")
+    current_platform.check(dev.index if dev is not None else None)
+
+
+def mixed_precision_gemm(
+    x: torch.Tensor,
+    w_q_packed: torch.Tensor,
+    w_s: torch.Tensor,
+    w_zp: torch.Tensor | None,
+    weight_size_bits: int,
+    weight_bias: int,
+    group_size: int,
+    *,
+    output_dtype: torch.dtype | None = None,
+    acc_dtype: torch.dtype | None = None,
+    meta_dtype: torch.dtype | None = None,
+    scaled_activations: bool = False,
+    strict: bool = False,
+    variant: int = _lib.AUTO,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """Mixed precision GEMM: `x[M,K] @ dequant(w_q_packed[K/pf,N], w_s, w_zp) -> [M,N]`.
+
+    Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus two optional keywords:
+    `variant` forces a kernel family (debug / benchmarking), `out` reuses a caller-owned output buffer.
+    """
+    _require_device(x, w_q_packed, w_s, w_zp)
+    metadata = create_mixed_precision_metadata(
+        x, w_q_packed, w_s, w_zp, weight_size_bits, weight_bias, group_size,
+        output_dtype=output_dtype, acc_dtype=acc_dtype, meta_dtype=meta_dtype,
+        scaled_activations=scaled_activations, strict=strict,
+    )  # fmt: skip
+    if not metadata.data_contiguous:
+        # the reference honours arbitrary strides (gemm.py:518-525); the CUDA kernels want dense row-major
+        x, w_q_packed, w_s = x.contiguous(), w_q_packed.contiguous(), w_s.contiguous()
+        w_zp = None if w_zp is None else w_zp.contiguous()
+    if out is None:
+        out = torch.empty((metadata.m_dim, metadata.n_dim), device=x.device, dtype=metadata.output_dtype)
+    elif tuple(out.shape) != (metadata.m_dim, metadata.n_dim) or out.dtype != metadata.output_dtype or not out.is_contiguous():
+        raise ValueError("`out` must be a contiguous [M, N] tensor of the output dtype")
+    if metadata.m_dim == 0:
+        return out
+    mixed_precision_gemm_launcher(out, x, w_q_packed, w_s, w_zp, metadata, variant=variant)
+    return out
+
+
+def dequantize_weights(
+    w_q_packed: torch.Tensor,
+    w_s: torch.Tensor,
+    w_zp: torch.Tensor | None,
+    weight_size_bits: int,
+    weight_bias: int,
+    group_size: int,
+) -> torch.Tensor:
+    """W[K,N] in `w_s.dtype`, bit-identical to the reference quantiser's `w_ref`
+    (conch/third_party/vllm/quant_utils.py:74) -- the `_dequantize` stage run on its own."""
+    _require_device(w_q_packed, w_s, w_zp)
+    pf = 32 // weight_size_bits
+    k_dim, n_dim = w_q_packed.shape[0] * pf, w_q_packed.shape[1]
+    if group_size == -1:
+        group_size = k_dim
+    if w_s.dtype not in _ACT_DTYPES:
+        raise NotImplementedError(f"scale dtype {w_s.dtype}")
+    if tuple(w_s.shape) != (k_dim // group_size, n_dim):
+        raise ValueError(f"Invalid w_s shape {tuple(w_s.shape)}")
+    out = torch.empty((k_dim, n_dim), device=w_q_packed.device, dtype=w_s.dtype)
+    dequantize_launcher(
+        out, w_q_packed.contiguous(), w_s.contiguous(), None if w_zp is None else w_zp.contiguous(),
+        weight_size_bits, weight_bias, group_size,
+    )  # fmt: skip
+    return out

@@ -1,0 +1,114 @@
+/*
+ * conch_b200.h -- C ABI of the B200-native mixed-precision GEMM library (libconch_b200.so).
+ *
+ * This is the drop-in boundary for ONE reference path:
+ *   conch.ops.quantization.gemm.mixed_precision_gemm      (reference conch/ops/quantization/gemm.py:133-168)
+ *     -> mixed_precision_gemm_launcher                     (reference conch/kernels/quantization/gemm.py:482-545)
+ *     -> Triton _gemm_kernel + _dequantize                 (reference conch/kernels/quantization/gemm.py:176-457)
+ * Every entry point below replaces the Triton launch `_gemm_kernel[grid](...)` at
+ * conch/kernels/quantization/gemm.py:500-545 (or, for cb200_dequantize, the `_dequantize` stage at :176-216
+ * run on its own as a test aid).  The host side that binds it is conch_b200/_lib.py (ctypes); the stub a
+ * maintainer of the reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`.
+ *   - the caller owns every buffer (inputs, `out`, `workspace`); nothing is allocated or freed here,
+ *     nothing synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*), so every
+ *     call is CUDA-graph capturable.
+ *   - return value: 0 = success; < 0 = cb200_status (argument / unsupported); > 0 = cudaError_t.
+ *     cb200_last_error() returns a thread-local human readable message for the last non-zero return.
+ *   - tensors are dense row-major:
+ *        x            [M, K]      fp16 | bf16                      (reference arg `x`)
+ *        w_q_packed   [K/pf, N]   int32, pf = 32/bits, value k = pf*row + i sits in bits [bits*i, bits*(i+1))
+ *                                                                  (reference conch/third_party/vllm/quant_utils.py:104-125)
+ *        w_s          [K/g, N]    same dtype as x                  (reference arg `w_s`)
+ *        w_zp         [K/g, N]    int32 | uint8 | dtype of x, or 1 element, or NULL
+ *        out          [M, N]      fp16 | bf16 | fp32
+ *     W[k,n] = RN_act( (q[k,n] - weight_bias - zp[k/g,n]) * s[k/g,n] ),  out = cast(sum_k fp32(x[m,k] * W[k,n]))
+ *                                                                  (reference conch/kernels/quantization/gemm.py:192-216, 401, 443-457)
+ */
+#ifndef CONCH_B200_H_
+#define CONCH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_VERSION 100 /* 1.0.0 */
+
+#if defined(__GNUC__)
+#define CB200_API __attribute__((visibility("default")))
+#else
+#define CB200_API
+#endif
+
+/* element types (activations, scales, outputs) */
+enum cb200_dtype { CB200_F16 = 0, CB200_BF16 = 1, CB200_F32 = 2 };
+
+/* what `w_zp` points at (reference: w_zp None / int32 from quantize_weights / uint8 from vLLM / meta dtype) */
+enum cb200_zp_kind { CB200_ZP_NONE = 0, CB200_ZP_I32 = 1, CB200_ZP_U8 = 2, CB200_ZP_ACT = 3 };
+
+/* kernel families; 0 lets the library choose by regime */
+enum cb200_variant {
+  CB200_AUTO = 0,
+  CB200_DECODE_MMA = 1,   /* M <= 16 per pass: split-K skinny GEMM, 64/128-bit weight loads, in-register dequant, HMMA dot, smem + last-CTA reduce */
+  CB200_TC_SS = 2,        /* tcgen05: TMA -> smem dequant (K-major, 128B swizzle) -> UMMA (both operands smem), TMEM accumulators */
+  CB200_TC_TS = 3,        /* tcgen05: TMA -> dequant straight into TMEM (W is the TMEM A operand), x tile from smem */
+  CB200_TC2_TS = 4        /* as TC_TS on a 2-CTA pair (cta_group::2), persistent */
+};
+
+enum cb200_status {
+  CB200_OK = 0,
+  CB200_ERR_ARG = -1,         /* null / misaligned pointer, non-positive size             -> ValueError        */
+  CB200_ERR_SHAPE = -2,       /* K, N or group_size outside the supported lattice         -> ValueError        */
+  CB200_ERR_UNSUPPORTED = -3, /* bits not in {4,8}, dtype combination not implemented     -> NotImplementedError */
+  CB200_ERR_WORKSPACE = -4,   /* workspace too small for the chosen variant               -> ValueError        */
+  CB200_ERR_DEVICE = -5       /* not an sm_100 device / driver entry point missing        -> RuntimeError      */
+};
+
+CB200_API int cb200_version(void);
+CB200_API const char* cb200_last_error(void);
+
+/* Bytes of scratch cb200_mpgemm may need for this problem (split-K partial sums + arrival counters).
+ * The first CB200_WORKSPACE_COUNTER_BYTES bytes hold counters and MUST be zero before the first use;
+ * kernels leave them zero again on exit, so the buffer can be reused forever without a memset. */
+#define CB200_WORKSPACE_COUNTER_BYTES 65536
+CB200_API size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_size_bits, int variant);
+
+/* out[M,N] = x[M,K] @ dequant(w_q_packed, w_s, w_zp).
+ * Replaces: mixed_precision_gemm_launcher(output, x, w_q_packed, w_s, w_zp, metadata)
+ *           (reference conch/kernels/quantization/gemm.py:482-545).
+ * group_size: elements of K sharing one scale row; -1 or K = per-channel.  Must be a multiple of 64 (or K),
+ * like the reference kernel (its BK=64 K-block picks ONE scale row, gemm.py:329,354).  K % 64 == 0, N % 64 == 0. */
+CB200_API int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
+                 int64_t M, int64_t K, int64_t N,
+                 int weight_size_bits, int weight_bias, int64_t group_size,
+                 int act_dtype, int out_dtype, int zp_kind, int zp_is_scalar,
+                 void* workspace, size_t workspace_bytes,
+                 int variant, void* stream);
+
+/* Which kernel family the last cb200_mpgemm call on this thread dispatched to (a cb200_variant), and how many
+ * kernel launches it enqueued.  Used by tests and by bench.py's `gpu_launches` accounting. */
+CB200_API int cb200_last_variant(void);
+CB200_API int cb200_last_launch_count(void);
+
+/* w_out[K,N] (act dtype) = dequant(w_q_packed, w_s, w_zp): the `_dequantize` stage alone
+ * (reference conch/kernels/quantization/gemm.py:176-216) -- bit-exact against the reference's w_ref. */
+CB200_API int cb200_dequantize(const void* w_q_packed, const void* w_s, const void* w_zp, void* w_out,
+                     int64_t K, int64_t N,
+                     int weight_size_bits, int weight_bias, int64_t group_size,
+                     int act_dtype, int zp_kind, int zp_is_scalar, void* stream);
+
+/* Debug/tuning knobs: override the decode kernel's tiling (0 = heuristic).  Process-global, not thread-safe. */
+CB200_API void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_words);
+/* Debug/tuning knobs for the tcgen05 family: m_tile (MMA N: 16..256, 0 = heuristic), split_k (0 = heuristic). */
+CB200_API void cb200_set_tc_tuning(int m_tile, int split_k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONCH_B200_H_ */

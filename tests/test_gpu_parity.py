@@ -1,0 +1,252 @@
+"""GPU parity tests (run with -m gpu on a B200).  Every call goes through the C ABI (ctypes -> libconch_b200.so).
+
+  * dequantised weights: BIT-EXACT against the reference's w_ref (golden fixtures) and against the CPU oracle;
+  * GEMM output: rtol = atol = 1e-2 against the oracle's fp32-accumulated result (north_star tolerance), and the
+    reference's own looser tolerance against its `torch.matmul(a, w_ref)` fixture.
+"""
+
+from __future__ import annotations
+
+import math
+
+import pytest
+import torch
+
+import mpgemm_oracle as oracle
+from conch_b200 import _lib
+from conch_b200.ops.quantization.gemm import dequantize_weights, mixed_precision_gemm
+from helpers import ATOL, DTYPES, RTOL, assert_gemm_close, bits, golden_id, golden_index, load_golden, to_cuda
+
+pytestmark = pytest.mark.gpu
+INDEX = golden_index()
+
+ALL_VARIANTS = [_lib.DECODE_MMA]
+
+
+def _variants_for(m: int) -> list[int]:
+    lib = _lib.load()  # noqa: F841
+    return ALL_VARIANTS
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded(built_lib):
+    """The tests must exercise the in-tree CUDA library, never a fallback."""
+    lib = _lib.load()
+    assert lib.cb200_version() == 100
+    assert torch.cuda.is_available() and torch.cuda.get_device_capability()[0] == 10
+    yield
+    with open("/proc/self/maps") as f:
+        assert "libconch_b200.so" in f.read()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# golden fixtures (produced by the real reference)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("entry", INDEX, ids=golden_id)
+def test_dequant_bit_exact_vs_reference_fixture(entry):
+    g = load_golden(entry)
+    wq, ws, wzp = to_cuda(g["w_q_packed"], g["w_s"], g["w_zp"])
+    w = dequantize_weights(wq, ws, wzp, entry["bits"], entry["bias"], entry["group_size"])
+    assert w.dtype == DTYPES[entry["dtype"]]
+    assert torch.equal(bits(w), bits(g["w_ref"]))
+    if wzp is not None:  # vLLM-style uint8 zero-points and activation-dtype zero-points: same bits
+        for z in (wzp.to(torch.uint8), wzp.to(w.dtype)):
+            w2 = dequantize_weights(wq, ws, z, entry["bits"], entry["bias"], entry["group_size"])
+            assert torch.equal(bits(w2), bits(g["w_ref"]))
+
+
+@pytest.mark.parametrize("entry", INDEX, ids=golden_id)
+def test_gemm_vs_reference_fixture(entry):
+    g = load_golden(entry)
+    x, wq, ws, wzp = to_cuda(g["x"], g["w_q_packed"], g["w_s"], g["w_zp"])
+    want = oracle.mixed_precision_gemm_ref(g["x"], g["w_q_packed"], g["w_s"], g["w_zp"], entry["bits"], entry["bias"], entry["group_size"])
+    for variant in _variants_for(x.shape[0]):
+        out = mixed_precision_gemm(x, wq, ws, wzp, entry["bits"], entry["bias"], entry["group_size"], variant=variant)
+        assert out.shape == (entry["m"], entry["n"]) and out.dtype == x.dtype
+        assert_gemm_close(out, want, f"variant {variant}")
+        # the reference's own tolerance against its own matmul(a, w_ref) output
+        atol = min(5e-2 * math.sqrt(entry["k"]), 1)
+        torch.testing.assert_close(out.cpu().float(), g["out_ref_matmul"].float(), rtol=1e-1, atol=atol)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# seeded problems vs the CPU oracle
+# ------------------------------------------------------------------------------------------------------------
+def _run_case(m, k, n, wname, g, dtype, zp, recipe="llama", seed=0, variant=_lib.AUTO, zp_as=None, out_dtype=None):
+    p = oracle.make_problem(m, k, n, wname, g, dtype, zp, seed=seed, recipe=recipe)
+    w_zp = p.w_zp
+    if w_zp is not None and zp_as is not None:
+        w_zp = w_zp.to(zp_as)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, w_zp)
+    w = dequantize_weights(wq, ws, wzp, p.wtype.bits, p.wtype.bias, g)
+    assert torch.equal(bits(w), bits(p.w_ref)), "dequantised weights must be bit-exact"
+    out = mixed_precision_gemm(x, wq, ws, wzp, p.wtype.bits, p.wtype.bias, g, variant=variant, output_dtype=out_dtype)
+    want = oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, p.wtype.bits, p.wtype.bias, g, output_dtype=out_dtype)
+    assert out.dtype == (out_dtype or dtype)
+    assert_gemm_close(out, want, f"{m}x{k}x{n} {wname} g={g} {dtype} zp={zp} variant={variant}")
+    return out
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 7, 8, 9, 15, 16])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("wname", ["uint4", "uint4b8", "uint8", "uint8b128"])
+def test_decode_rows(m, dtype, wname):
+    _run_case(m, 1024, 512, wname, 128, dtype, True)
+
+
+@pytest.mark.parametrize("k,n", [(4096, 4096), (4096, 6144), (14336, 4096), (4096, 28672)], ids=["o", "qkv", "down", "gate_up"])
+@pytest.mark.parametrize("m", [1, 4, 16])
+def test_llama3_8b_decode_shapes(k, n, m):
+    """BASELINE config 2: W4A16, int4 asymmetric (uint4 + zero-points), g=128, fp16."""
+    _run_case(m, k, n, "uint4", 128, torch.float16, True)
+
+
+@pytest.mark.parametrize("g", [64, 128, 256, -1])
+@pytest.mark.parametrize("zp", [True, False], ids=["zp", "sym"])
+@pytest.mark.parametrize("wname", ["uint4b8", "uint8b128"])
+def test_group_sizes(g, zp, wname):
+    _run_case(5, 1024, 256, wname, g, torch.bfloat16, zp)
+
+
+@pytest.mark.parametrize("zp_as", [torch.uint8, torch.float16], ids=["zp_u8", "zp_f16"])
+@pytest.mark.parametrize("wname", ["uint4", "uint8"])
+def test_zero_point_dtypes(zp_as, wname):
+    _run_case(3, 512, 256, wname, 128, torch.float16, True, zp_as=zp_as)
+
+
+def test_scalar_zero_point():
+    p = oracle.make_problem(4, 512, 256, "uint4", 128, torch.float16, False, seed=5)
+    zp = torch.tensor([[7]], dtype=torch.int32)
+    x, wq, ws, z = to_cuda(p.x, p.w_q_packed, p.w_s, zp)
+    out = mixed_precision_gemm(x, wq, ws, z, 4, 0, 128)
+    want = oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, zp, 4, 0, 128)
+    assert_gemm_close(out, want)
+    w = dequantize_weights(wq, ws, z, 4, 0, 128)
+    assert torch.equal(bits(w), bits(oracle.dequantize(p.w_q_packed, p.w_s, zp, 4, 0, 128, torch.float16)))
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_output_dtype_override(out_dtype):
+    _run_case(2, 512, 256, "uint4", 128, torch.float16, True, out_dtype=out_dtype)
+
+
+def test_non_contiguous_inputs_and_out_buffer():
+    p = oracle.make_problem(6, 512, 256, "uint4b8", 128, torch.float16, True, seed=2)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    x_nc = torch.empty((6, 1024), device="cuda", dtype=torch.float16)[:, ::2]
+    x_nc.copy_(x)
+    assert not x_nc.is_contiguous()
+    buf = torch.empty((6, 256), device="cuda", dtype=torch.float16)
+    out = mixed_precision_gemm(x_nc, wq, ws, wzp, 4, 8, 128, out=buf)
+    assert out.data_ptr() == buf.data_ptr()
+    assert_gemm_close(out, oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, 4, 8, 128))
+
+
+def test_m_zero_and_unsupported_shapes():
+    p = oracle.make_problem(1, 512, 256, "uint4", 128, torch.float16, True)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    assert mixed_precision_gemm(x[:0], wq, ws, wzp, 4, 0, 128).shape == (0, 256)
+    with pytest.raises(ValueError):  # N not a multiple of 64 (outside the reference kernel's domain too)
+        mixed_precision_gemm(x, wq[:, :200].contiguous(), ws[:, :200].contiguous(), wzp[:, :200].contiguous(), 4, 0, 128)
+
+
+def test_split_k_workspace_is_reusable_and_deterministic():
+    """Cross-CTA split-K uses self-resetting arrival counters: repeated calls must agree bit for bit."""
+    lib = _lib.load()
+    p = oracle.make_problem(16, 14336, 256, "uint4", 128, torch.float16, True, seed=3)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    want = oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, 4, 0, 128)
+    try:
+        lib.cb200_set_decode_tuning(0, 0, 8, 0)
+        first = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.DECODE_MMA)
+        for _ in range(5):
+            again = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.DECODE_MMA)
+            assert torch.equal(again, first)
+    finally:
+        lib.cb200_set_decode_tuning(0, 0, 0, 0)
+    assert_gemm_close(first, want)
+
+
+@pytest.mark.parametrize("vec", [2, 4])
+@pytest.mark.parametrize("warps", [(1, 16), (2, 8), (4, 4), (1, 8), (2, 2)])
+def test_decode_tilings(vec, warps):
+    lib = _lib.load()
+    try:
+        lib.cb200_set_decode_tuning(warps[0], warps[1], 0, vec)
+        for m in (1, 12):
+            _run_case(m, 2048, 512, "uint4", 128, torch.float16, True, variant=_lib.DECODE_MMA)
+            _run_case(m, 1024, 256, "uint8b128", 128, torch.bfloat16, True, variant=_lib.DECODE_MMA)
+    finally:
+        lib.cb200_set_decode_tuning(0, 0, 0, 0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference's own test matrix (tests/mixed_precision_gemm_test.py:36-77), re-run against this op
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(("m_dim", "k_dim", "n_dim"), [(128, 256, 128), (1024, 1024, 1024)])
+@pytest.mark.parametrize("weight_dtype", ["uint4b8", "uint8b128", "uint4", "uint8"])
+@pytest.mark.parametrize("use_zero_points", [True, False])
+@pytest.mark.parametrize("input_dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_reference_matrix(m_dim, k_dim, n_dim, weight_dtype, use_zero_points, input_dtype):
+    p = oracle.make_problem(m_dim, k_dim, n_dim, weight_dtype, 128, input_dtype, use_zero_points, seed=0, recipe="reference")
+    a, w_q_packed, w_s, w_zp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    output_ref = oracle.reference_test_expression(p.x, p.w_ref)  # torch.matmul(a, w_ref), as the reference test does
+    output = mixed_precision_gemm(a, w_q_packed, w_s, w_zp, p.wtype.bits, p.wtype.bias, 128)
+    atol = min(5e-2 * math.sqrt(k_dim), 1)
+    torch.testing.assert_close(output.cpu(), output_ref, rtol=1e-1, atol=atol)  # the reference's tolerance
+    want = oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, p.wtype.bits, p.wtype.bias, 128)
+    assert_gemm_close(output, want)  # the north_star tolerance
+
+
+# ------------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE's full sizes (no CPU oracle needed)
+# ------------------------------------------------------------------------------------------------------------
+def _torch_dequant_gpu(wq, ws, wzp, bits_, bias, g):
+    """Plain-PyTorch restatement on the GPU (integer unpack is exact; one rounding in the multiply)."""
+    pf = 32 // bits_
+    kp, n = wq.shape
+    shifts = (torch.arange(pf, device=wq.device, dtype=torch.int32) * bits_).view(1, pf, 1)
+    q = ((wq.view(kp, 1, n) >> shifts) & ((1 << bits_) - 1)).reshape(kp * pf, n)
+    v = q - bias
+    if wzp is not None:
+        v = v - wzp.to(torch.int32).repeat_interleave(g, dim=0)
+    return v.to(ws.dtype) * ws.repeat_interleave(g, dim=0)
+
+
+@pytest.mark.parametrize("k,n", [(4096, 28672), (14336, 4096), (8192, 28672)], ids=["8b_gate_up", "8b_down", "70b_ffn"])
+def test_full_size_row_selection_and_dequant(k, n):
+    """x = one-hot rows  =>  out[i, :] == W[k_i, :] exactly; and the dequant kernel equals a torch restatement."""
+    from conch_b200 import quant_utils
+
+    wq, ws, wzp = quant_utils.random_packed_weights(k, n, quant_utils.scalar_types.uint4, 128, torch.float16, "cuda", seed=1)
+    w = dequantize_weights(wq, ws, wzp, 4, 0, 128)
+    assert torch.equal(w, _torch_dequant_gpu(wq, ws, wzp, 4, 0, 128))
+    rows = [0, 1, 7, 8, 127, 128, k // 2 + 3, k - 1]
+    for m in (1, 8):
+        x = torch.zeros((m, k), device="cuda", dtype=torch.float16)
+        for i in range(m):
+            x[i, rows[i]] = 1.0
+        out = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128)
+        assert torch.equal(out, w[rows[:m]])
+    # linearity in x (fp32 accumulate): f(2x) == 2 f(x) exactly, f(x1) + f(x2) ~= f(x1 + x2)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x1 = torch.randn((4, k), generator=gen, device="cuda", dtype=torch.float16)
+    f1 = mixed_precision_gemm(x1, wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)
+    f2 = mixed_precision_gemm(x1 * 2, wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)
+    assert torch.equal(f2, f1 * 2)
+    ref = x1.float() @ w.float()
+    torch.testing.assert_close(f1, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_batch_rows_equal_single_rows():
+    """Row m of an M=16 call equals the M=1 call on that row (same weights, same K order)."""
+    from conch_b200 import quant_utils
+
+    k, n = 4096, 6144
+    wq, ws, wzp = quant_utils.random_packed_weights(k, n, quant_utils.scalar_types.uint4, 128, torch.float16, "cuda", seed=2)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((16, k), generator=gen, device="cuda", dtype=torch.float16)
+    full = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)
+    for i in (0, 5, 15):
+        one = mixed_precision_gemm(x[i : i + 1].contiguous(), wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)
+        torch.testing.assert_close(one[0], full[i], rtol=1e-4, atol=1e-4)
