@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the mixed-precision GEMM hot path (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): one Llama-3-8B W4A16 decode token, M=1 -- the four quantised projections
+(qkv 4096->6144, o 4096->4096, gate_up 4096->28672, down 14336->4096; uint4 + int32 zero-points, group_size 128,
+fp16 activations) of all 32 layers = 128 GEMV launches reading 3.49 GB of packed weights (>> the 126 MB L2, so every
+step streams its weights from HBM).  A "step" is one such token.
+
+  value     whole-job HBM GB/s over the algorithmic bytes (packed weights + activations), inputs resident in HBM,
+            the 128 launches replayed from a CUDA graph, CUDA-event timed, max over ranks.
+  e2e       the same metric through the public Python op, call by call, x in pinned host memory, H2D of the step's
+            activations and D2H of the step's outputs inside the timed region (wall clock, synchronised both sides).
+  roofline  the decode kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference
+            the reference's PyTorch path (`torch.matmul(x, w_ref)`, tests/mixed_precision_gemm_test.py:70) restated by
+            the oracle, on this box's host cores, on a bounded sample (one layer's four projections per step).
+Multi-GPU (N > 1): weak scaling -- every rank owns an equally sized column (N) shard of an N-times wider layer, runs
+the same per-GPU step and all-gathers the outputs of every GEMM over NCCL (the path's only exchange step).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+LAYERS = 32
+# (name, K, N) of Llama-3-8B's quantised projections
+PROJECTIONS = (("qkv", 4096, 6144), ("o", 4096, 4096), ("gate_up", 4096, 28672), ("down", 14336, 4096))
+BITS, BIAS, GROUP = 4, 0, 128
+M = 1
+WORKLOAD = "llama3-8b-w4a16-decode-M1-32layers(qkv,o,gate_up,down;uint4+zp_int32;g128;fp16)"
+METRIC = "W4A16 GEMM HBM GB/s, Llama-3-8B decode shapes M=1 (algorithmic bytes: packed weights + activations)"
+
+
+def algorithmic_bytes(m: int = M) -> int:
+    """B_W + B_X = K*N*bits/8 + M*K*2 per GEMM."""
+    return LAYERS * sum(k * n * BITS // 8 + m * k * 2 for _, k, n in PROJECTIONS)
+
+
+def flops(m: int = M) -> int:
+    return LAYERS * sum(2 * m * k * n for _, k, n in PROJECTIONS)
+
+
+def measured_peaks() -> tuple[float, str, dict]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML; nvidia-smi -lms cannot resolve a millisecond-scale timed region)
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples: list[int] = []
+        self.reasons: set[str] = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nv = None
+
+    _NAMES = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }  # fmt: skip
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self._NAMES.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.001)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": s[len(s) // 2] if s else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's PyTorch path restated by the oracle (the one place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference(steps: int, warmup: int) -> dict:
+    import torch
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import mpgemm_oracle as oracle
+
+    threads = torch.get_num_threads()
+    gen = torch.Generator().manual_seed(0)
+    layers = []
+    for name, k, n in PROJECTIONS:
+        packed = torch.randint(-(1 << 31), (1 << 31) - 1, (k // 8, n), generator=gen, dtype=torch.int64).to(torch.int32)
+        w_s = (0.004 + 0.004 * torch.rand((k // GROUP, n), generator=gen)).to(torch.float16)
+        w_zp = torch.randint(5, 11, (k // GROUP, n), generator=gen, dtype=torch.int32)
+        w_ref = oracle.dequantize(packed, w_s, w_zp, BITS, BIAS, GROUP, torch.float16)  # offline, like the reference test
+        x = torch.randn((M, k), generator=gen).to(torch.float16)
+        layers.append((x, w_ref))
+    sample_bytes = sum(k * n * BITS // 8 + M * k * 2 for _, k, n in PROJECTIONS)  # one layer = 1/32 of a step
+
+    def one():
+        for x, w_ref in layers:
+            oracle.reference_test_expression(x, w_ref)  # torch.matmul(a, w_ref), tests/mixed_precision_gemm_test.py:70
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return {
+        "value": sample_bytes / dt / 1e9,
+        "unit": "GB/s",
+        "cores": threads,
+        "host_cpus": os.cpu_count(),
+        "kind": "port",
+        "sample": "one Llama-3-8B layer's four M=1 projections per step (1/32 of the GPU step), fp16 torch.matmul(x, w_ref) "
+        "with w_ref pre-dequantised offline exactly as the reference test does; rate metric, so no rescaling",
+        "ms_per_sample": dt * 1e3,
+    }
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 50))
+    res = cpu_reference(steps, max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": res["value"],
+        "unit": "GB/s",
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)),
+        "ms_per_step": res["ms_per_sample"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "device": "host CPU", "l2": "n/a"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")},
+        "e2e": {"value": res["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from conch_b200 import _lib, quant_utils
+    from conch_b200.build import build
+    from conch_b200.ops.quantization.gemm import mixed_precision_gemm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build()  # no-op when the in-tree .so matches the sources
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+
+    # ---- synthetic model: 32 layers x 4 projections, drawn directly in the packed domain ------------------------
+    st = quant_utils.scalar_types.uint4
+    weights = []  # [layer][proj] -> (packed, w_s, w_zp)
+    for layer in range(LAYERS):
+        row = []
+        for pi, (_, k, n) in enumerate(PROJECTIONS):
+            row.append(quant_utils.random_packed_weights(k, n, st, GROUP, torch.float16, dev, seed=1000 * rank + 4 * layer + pi))
+        weights.append(row)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    xs = [torch.randn((M, k), generator=gen, device=dev, dtype=torch.float16) for _, k, _ in PROJECTIONS]
+    outs = [[torch.empty((M, n), device=dev, dtype=torch.float16) for _, _, n in PROJECTIONS] for _ in range(LAYERS)]
+    gathered = None
+    if world > 1:
+        gathered = [torch.empty((world, M, n), device=dev, dtype=torch.float16) for _, _, n in PROJECTIONS]
+
+    launches_per_step = 0
+
+    def step(count: bool = False):
+        nonlocal launches_per_step
+        for layer in range(LAYERS):
+            for pi in range(len(PROJECTIONS)):
+                packed, w_s, w_zp = weights[layer][pi]
+                mixed_precision_gemm(xs[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=outs[layer][pi])
+                if count:
+                    launches_per_step += lib.cb200_last_launch_count()
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered[pi], outs[layer][pi])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (eager), then capture one step into a CUDA graph ---------------------------------------------
+    step(count=True)
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    barrier()
+    stream = torch.cuda.Stream(device=dev)
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        with torch.cuda.stream(stream):
+            step()
+            stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                step()
+            for _ in range(max(3, args.warmup)):
+                graph.replay()
+        barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ------------------------------------
+    with torch.cuda.stream(stream):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with ClockSampler(local_rank) as clocks:
+            start.record(stream)
+            for _ in range(args.steps):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    step()
+            stop.record(stream)
+            stop.synchronize()
+        barrier()
+    ms = start.elapsed_time(stop)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    bytes_step = algorithmic_bytes() * world
+    value = bytes_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the public op: pinned host activations in, outputs back, every step ----------------
+    x_host = [x.cpu().pin_memory() for x in xs]
+    out_dev = torch.empty((LAYERS, sum(n for _, _, n in PROJECTIONS)), device=dev, dtype=torch.float16)
+    out_host = torch.empty(out_dev.shape, dtype=torch.float16).pin_memory()
+    col0 = [0]
+    for _, _, n in PROJECTIONS:
+        col0.append(col0[-1] + n)
+    out_views = [[out_dev[layer : layer + 1, col0[pi] : col0[pi + 1]] for pi in range(len(PROJECTIONS))] for layer in range(LAYERS)]
+    # column slices of a row-major buffer are not contiguous for M>1, but with M=1 each view is one dense row segment
+    x_dev = [torch.empty_like(x) for x in xs]
+
+    def e2e_step():
+        for pi in range(len(PROJECTIONS)):
+            x_dev[pi].copy_(x_host[pi], non_blocking=True)
+        for layer in range(LAYERS):
+            for pi in range(len(PROJECTIONS)):
+                packed, w_s, w_zp = weights[layer][pi]
+                mixed_precision_gemm(x_dev[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=out_views[layer][pi].view(M, -1))
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered[pi], out_views[layer][pi].view(M, -1))
+        out_host.copy_(out_dev, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = bytes_step / float(t.item()) / 1e9
+    h2d = sum(x.numel() * 2 for x in xs)
+    d2h = out_dev.numel() * 2
+
+    # ---- report --------------------------------------------------------------------------------------------------
+    if rank == 0:
+        peak, peak_src, peaks = measured_peaks()
+        per_gpu = value / world
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("decode_kernel_dram_bytes_per_launch")
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": "GB/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f16",
+            "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD,
+                "M": M,
+                "launch": "cuda-graph replay of the 128 GEMV launches" if graph is not None else "eager python launches",
+                "l2": "inputs larger than L2: 3.49 GB of packed weights per step vs 126 MB L2",
+                "sharding": "none" if world == 1 else f"N-sharded x{world}, NCCL all_gather_into_tensor after every GEMM",
+            },
+            "tflops": flops() * world / (ms_per_step * 1e-3) / 1e12,
+            "roofline": {
+                "bound": "hbm",
+                "achieved": per_gpu,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": per_gpu / peak,
+                "traffic": traffic,
+                "peak_source": peak_src,
+                "kernel": "cb200::decode_kernel<__half,4,1,2,false>",
+                "algorithmic_bytes_per_launch": algorithmic_bytes() / (LAYERS * len(PROJECTIONS)),
+                "avg_launch_us": ms_per_step * 1e3 / (LAYERS * len(PROJECTIONS)),
+            },
+            "e2e": {
+                "value": e2e_value,
+                "unit": "GB/s",
+                "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(t.item()) * 1e3,
+                "steps": e2e_steps,
+                "path": "conch_b200.mixed_precision_gemm called 128x per step from Python, pinned-host x -> device, outputs -> pinned host",
+            },
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = cpu_reference(steps=5, warmup=1)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--no-graph", action="store_true", help="time eager Python launches instead of a CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
