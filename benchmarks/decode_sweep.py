@@ -36,7 +36,7 @@ def main() -> None:
     st = getattr(quant_utils.scalar_types, args.wtype)
     tilings = [(0, 0, 0, 0)]
     if not args.quick:
-        tilings += [(wn, wk, ks, vec) for vec in (2, 4) for (wn, wk) in ((1, 16), (1, 8), (2, 8), (2, 4), (4, 4), (1, 4)) for ks in (1, 2, 4)]
+        tilings += [(mode, 0, upw, 0) for mode in (1, 2) for upw in (0, 1, 2, 3, 4, 8)]
     rows = []
     with open(args.out, "w") as f:
         for name, m in itertools.product(args.shapes.split(","), [int(v) for v in args.ms.split(",")]):

@@ -104,9 +104,9 @@ void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_word
 void cb200_set_tc_tuning(int m_tile, int split_k) { g_tc_tuning = {m_tile, split_k}; }
 
 size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_size_bits, int variant) {
-  (void)weight_size_bits;
   (void)variant;
-  const size_t a = decode_workspace_bytes(M, K, N);
+  const int bits = weight_size_bits == 8 ? 8 : 4;
+  const size_t a = decode_workspace_bytes(M, K, N, bits);
   const size_t b = tc_workspace_bytes(M, K, N);
   return a > b ? a : b;
 }

@@ -42,7 +42,7 @@ void set_error(const char* fmt, ...);
 int launch_dequant(const Problem& p, int bits, int act_dtype, cudaStream_t stream);
 int launch_decode(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream,
                   int* launches);
-size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N);
+size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
 int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, size_t ws_bytes,
               cudaStream_t stream, int* launches);
 size_t tc_workspace_bytes(int64_t M, int64_t K, int64_t N);

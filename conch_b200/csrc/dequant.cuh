@@ -111,10 +111,13 @@ __device__ __forceinline__ ColQ make_colq(A scale, float zb, A zpf) {
   return c;
 }
 
-// One packed word -> pf/2 pair registers of dequantised activations-dtype weights.
-template <class A, int BITS, Order ORD, bool FZP>
-__device__ __forceinline__ void dequant_word(uint32_t w, const ColQ& c, uint32_t (&out)[16 / BITS]) {
-  using Ops = ActOps<A>;
+// One packed word -> pf/2 pair registers.  SCALE=true: dequantised weights RN((q - zb) * s) (the reference's W);
+// SCALE=false: the exact integers (q - zb) in the activation dtype (the caller applies the scale elsewhere).
+template <class A, int BITS, Order ORD, bool FZP, bool SCALE>
+__device__ __forceinline__ void dequant_word_core(uint32_t w, const ColQ& c, uint32_t (&out)[16 / BITS]) {
+  struct Ops : ActOps<A> {
+    static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return SCALE ? ActOps<A>::mul(a, b) : a; }
+  };
   if constexpr (std::is_same<A, __half>::value && BITS == 4 && ORD == Order::Lop) {
     // fp16 magic: 0x6400 | q = 1024 + q ; 0x6400 | (q << 4) = 1024 + 16 q   (both exact in fp16)
     const uint32_t t = w >> 8;
@@ -191,11 +194,20 @@ __device__ __forceinline__ void dequant_word(uint32_t w, const ColQ& c, uint32_t
         out[i] = Ops::mul(v, c.s);
       }
     } else {
-      const float s = __uint_as_float(c.s);
+      const float s = SCALE ? __uint_as_float(c.s) : 1.f;
 #pragma unroll
       for (int i = 0; i < 2; ++i) out[i] = Ops::pair(f[2 * i] * s, f[2 * i + 1] * s);
     }
   }
+}
+
+template <class A, int BITS, Order ORD, bool FZP>
+__device__ __forceinline__ void dequant_word(uint32_t w, const ColQ& c, uint32_t (&out)[16 / BITS]) {
+  dequant_word_core<A, BITS, ORD, FZP, true>(w, c, out);
+}
+template <class A, int BITS, Order ORD, bool FZP>
+__device__ __forceinline__ void dequant_word_int(uint32_t w, const ColQ& c, uint32_t (&out)[16 / BITS]) {
+  dequant_word_core<A, BITS, ORD, FZP, false>(w, c, out);
 }
 
 // ---- zero-point / scale fetch helpers -----------------------------------------------------------------

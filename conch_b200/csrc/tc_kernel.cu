@@ -1,12 +1,577 @@
-// tcgen05 prefill kernel -- placeholder until the pipeline lands.
+// Prefill-regime kernel: warp-specialised TMA -> dequant -> tcgen05.mma pipeline with TMEM accumulators.
+//
+// Replaces the reference's `_gemm_kernel` main loop (conch/kernels/quantization/gemm.py:337-401: register dequant in the
+// critical path of every `tl.dot`, 128x64x64 tile, 2 stages).  Orientation is swap-AB: the MMA computes
+//     D^T[n, m] = sum_k W^T[n, k] * x[m, k]
+// so the 128 TMEM lanes are 128 weight columns n and the MMA-N dimension is the activation tile m_tile (16..256).
+// That makes (a) every dequant thread own ONE weight column -- scale / zero-point live in registers, a packed word
+// (8 consecutive k of one column, conch/third_party/vllm/quant_utils.py:119-124) turns into one 16-byte K-major chunk,
+// (b) small M cheap (MMA-N = 16 instead of 112 wasted rows of a 128-row tile), (c) x a plain K-major TMA tile.
+//
+// Roles (384 threads):  warp 0 lane 0  TMA producer   (x tile, 128B-swizzled; packed W tile, 8|16 rows x 128 int32)
+//                       warp 1 lane 0  MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=m_tile, K=16)
+//                       warp 2         TMEM allocator
+//                       warps 4..11    dequant        (smem packed -> registers -> dequant_word() -> operand A)
+//                                      then epilogue  (tcgen05.ld -> cast -> global)
+// Operand A (dequantised W) goes either to shared memory in the canonical K-major SWIZZLE_128B layout (variant SS) or
+// straight into tensor memory with tcgen05.st (variant TS: the weights never touch shared memory again, which halves
+// the smem traffic per MMA -- the limiter of this kernel).
+// Barriers per stage: full_x (TMA tx), full_w (TMA tx), a_ready (8 dequant warps), empty (tcgen05.commit).
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
+#include "dequant.cuh"
 
 namespace cb200 {
+
 TcTuning g_tc_tuning = {0, 0};
-bool tc_supported(const Problem&, int) { return false; }
-size_t tc_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-int launch_tc(const Problem&, int, int, int, void*, size_t, cudaStream_t, int*) {
-  set_error("tcgen05 path not built");
-  return CB200_ERR_UNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  // bounded spin: a protocol bug becomes a trap (launch error) instead of a hung GPU
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile base 1024-byte aligned, 128-byte rows, 8-row atoms)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units            bits [0,14)
+  d |= uint64_t(1) << 16;                  // leading byte offset (unused for SW128 K-major)  [16,30)
+  d |= uint64_t(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B       bits [32,46)
+  d |= uint64_t(1) << 46;                  // descriptor version (sm_100)              bits [46,48)
+  d |= uint64_t(2) << 61;                  // layout type SWIZZLE_128B                 bits [61,64)
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------------------------
+struct TcParams {
+  Problem p;
+  int kblocks_total;   // K / 64
+  int kb_per_split;    // 64-wide K blocks per CTA along gridDim.z
+  float* ws_partial;   // [split][M][N] fp32 when gridDim.z > 1
+};
+
+template <int MT, int BITS, bool TS>
+struct TcCfg {
+  static constexpr int NTILE = 128;
+  static constexpr int KB = 64;
+  static constexpr int PF = 32 / BITS;
+  static constexpr int WROWS = KB / PF;                 // packed rows per stage: 8 (int4) / 16 (int8)
+  static constexpr int X_BYTES = MT * 128;              // MT rows x 64 halfs, 128B swizzle
+  static constexpr int W_BYTES = WROWS * NTILE * 4;
+  static constexpr int A_BYTES = TS ? 0 : NTILE * 128;  // dequantised W tile, K-major 128B swizzle
+  static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + A_BYTES;
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+  static constexpr int S_SMEM = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int S_TMEM = TS ? (512 - MT) / 32 : 8;
+  static constexpr int S0 = S_SMEM < S_TMEM ? S_SMEM : S_TMEM;
+  static constexpr int S = S0 > 8 ? 8 : S0;
+  static constexpr int A_COL0 = MT;                     // first TMEM column of the A ring (TS)
+  static constexpr int TMEM_NEED = MT + (TS ? S * 32 : 0);
+  static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = S * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
+  static_assert(S >= 2, "pipeline needs at least two stages");
+};
+
+template <class A, int BITS, int MT, bool TS, int ZK>
+__global__ void __launch_bounds__(384, 1)
+    tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, TcParams prm) {
+  using Cfg = TcCfg<MT, BITS, TS>;
+  constexpr int S = Cfg::S;
+  constexpr bool FZP = ZK == CB200_ZP_ACT;
+  constexpr int PAIRS = 16 / BITS;     // pair registers per packed word
+  constexpr int WPT = 32 / Cfg::PF;    // packed words per dequant thread per stage (32 k of one column): 4 | 8
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t x_base = smem_base;
+  const uint32_t a_base = x_base + S * Cfg::X_BYTES;
+  const uint32_t w_base = a_base + S * Cfg::A_BYTES;
+  const uint32_t bar_base = w_base + S * Cfg::W_BYTES;
+  auto full_x = [&](int s) { return bar_base + 8u * s; };
+  auto full_w = [&](int s) { return bar_base + 8u * (S + s); };
+  auto a_ready = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (3 * S + s); };
+  const uint32_t d_full = bar_base + 8u * (4 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (4 * S + 1);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+
+  const Problem& p = prm.p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * Cfg::NTILE;
+  const int m0 = blockIdx.y * MT;
+  const int kb0 = blockIdx.z * prm.kb_per_split;
+  const int kb1 = min(kb0 + prm.kb_per_split, prm.kblocks_total);
+  const int nk = kb1 - kb0;
+
+  // ---- one-time setup ------------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_w);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_x(s), 1);
+      mbar_init(full_w(s), 1);
+      mbar_init(a_ready(s), 8);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(d_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================================================
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        mbar_expect_tx(full_w(s), Cfg::W_BYTES);
+        tma_load_2d(w_base + s * Cfg::W_BYTES, &tmap_w, n0, (kb0 + it) * Cfg::WROWS, full_w(s));
+        mbar_expect_tx(full_x(s), Cfg::X_BYTES);
+        tma_load_2d(x_base + s * Cfg::X_BYTES, &tmap_x, (kb0 + it) * Cfg::KB, m0, full_x(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================================================
+    if (lane == 0) {
+      constexpr uint32_t fmt = std::is_same<A, __half>::value ? 0u : 1u;  // F16 / BF16
+      // instruction descriptor: D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major (bits 15,16 = 0),
+      // N>>3 at [17,23), M>>4 at [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(MT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full_x(s), ph);
+        mbar_wait(a_ready(s), ph);
+        tc_fence_after();
+        const uint64_t bdesc = make_sw128_desc(x_base + s * Cfg::X_BYTES);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {  // four K=16 MMAs per 64-wide stage: +32 bytes inside the swizzle atom
+          const uint32_t acc = (it | k4) != 0;
+          if constexpr (TS) {
+            umma_ts(tmem_base, tmem_base + Cfg::A_COL0 + s * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
+          } else {
+            const uint64_t adesc = make_sw128_desc(a_base + s * Cfg::A_BYTES);
+            umma_ss(tmem_base, adesc + uint64_t(k4 * 2), bdesc + uint64_t(k4 * 2), idesc, acc);
+          }
+        }
+        umma_commit(empty(s));  // frees x / packed-W / A slot s once these MMAs have read them
+      }
+      umma_commit(d_full);
+    }
+  } else if (warp >= 4) {
+    // ================================ dequant warps, then epilogue ==================================================
+    const int q = warp & 3;          // TMEM lane quarter this warp may touch
+    const int kh = (warp - 4) >> 2;  // which 32-k half of the 64-k stage
+    const int nl = q * 32 + lane;    // weight column inside the tile == TMEM lane
+    const int n = n0 + nl;
+    const bool n_ok = n < p.N;
+    const A* sp = reinterpret_cast<const A*>(p.s);
+    const int bpg = p.g / Cfg::KB;   // 64-k blocks per group (g % 64 == 0)
+    const int ngrp = p.K / p.g;
+    A raw_s = A(0.f), raw_zf = A(0.f);
+    float raw_z = 0.f;
+    if (ZK != CB200_ZP_NONE && p.zp_scalar) {
+      if constexpr (ZK == CB200_ZP_I32) raw_z = float(__ldg(reinterpret_cast<const int32_t*>(p.zp)));
+      if constexpr (ZK == CB200_ZP_U8) raw_z = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp)));
+      if constexpr (ZK == CB200_ZP_ACT) raw_zf = *reinterpret_cast<const A*>(p.zp);
+    }
+    const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
+    auto fetch_group = [&](int grp) {
+      if (grp >= ngrp) grp = ngrp - 1;
+      if (!n_ok) return;
+      const size_t idx = size_t(grp) * p.N + n;
+      raw_s = sp[idx];
+      if (zp_per_group) {
+        if constexpr (ZK == CB200_ZP_I32) raw_z = float(__ldg(reinterpret_cast<const int32_t*>(p.zp) + idx));
+        if constexpr (ZK == CB200_ZP_U8) raw_z = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp) + idx));
+        if constexpr (ZK == CB200_ZP_ACT) raw_zf = reinterpret_cast<const A*>(p.zp)[idx];
+      }
+    };
+    int grp = (kb0 * Cfg::KB) / p.g;
+    int left = 0;
+    bool first = true;
+    const int first_left = (grp + 1) * bpg - kb0;
+    fetch_group(grp);
+    ColQ cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, raw_z + float(p.bias), raw_zf);
+
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      if (left == 0) {
+        cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, raw_z + float(p.bias), raw_zf);
+        left = first ? first_left : bpg;
+        first = false;
+        ++grp;
+        fetch_group(grp);
+      }
+      --left;
+      mbar_wait(full_w(s), ph);
+      const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem_gen + (w_base - smem_base) + s * Cfg::W_BYTES);
+      uint32_t regs[16];
+#pragma unroll
+      for (int j = 0; j < WPT; ++j) {
+        const uint32_t word = wst[(kh * WPT + j) * Cfg::NTILE + nl];
+        uint32_t pr[PAIRS];
+        dequant_word<A, BITS, Order::Natural, FZP>(word, cq, pr);
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) regs[j * PAIRS + i] = pr[i];
+      }
+      if constexpr (TS) {
+        // lane nl of TMEM, columns [A_COL0 + 32 s + 16 kh, +16): 32 consecutive k of this column, 2 per 32-bit cell
+        tmem_st16(tmem_base + (uint32_t(q * 32) << 16) + Cfg::A_COL0 + s * 32 + kh * 16, regs);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        // row nl of the K-major tile: 16-byte chunk c holds k = 8c..8c+7; 128B swizzle: chunk ^= row & 7
+        const uint32_t row = a_base + s * Cfg::A_BYTES + nl * 128;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t c = kh * 4 + c4;
+          const uint32_t addr = row + ((c ^ (nl & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(regs[c4 * 4 + 0]), "r"(regs[c4 * 4 + 1]),
+                       "r"(regs[c4 * 4 + 2]), "r"(regs[c4 * 4 + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready(s));
+    }
+
+    // ---- epilogue: D^T[n, m] (lane = n, column = m) -> out[m, n] ------------------------------------------------------
+    mbar_wait(d_full, 0);
+    tc_fence_after();
+    constexpr int HALF = MT / 2;                     // columns (m) handled by this warp
+    constexpr int CH = HALF >= 32 ? 32 : HALF;       // columns per tcgen05.ld
+    const bool split = gridDim.z > 1;
+    float* part = split ? prm.ws_partial + size_t(blockIdx.z) * p.M * p.N : nullptr;
+#pragma unroll 1
+    for (int cb = 0; cb < HALF; cb += CH) {
+      const int col0 = kh * HALF + cb;
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + col0;
+      if constexpr (CH == 32) tmem_ld32(taddr, r);
+      if constexpr (CH == 16) tmem_ld16(taddr, r);
+      if constexpr (CH == 8) tmem_ld8(taddr, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int m = m0 + col0 + c;
+        if (m < p.M && n_ok) {
+          const float v = __uint_as_float(r[c]);
+          if (split) {
+            part[size_t(m) * p.N + n] = v;
+          } else {
+            store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, v);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// out[m, n] = cast(sum_z partial[z][m][n])
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t total, int splits,
+                                     int out_dtype) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += part[size_t(z) * total + i];
+    store_out<float>(out, out_dtype, size_t(i), v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+  });
+  return fn;
+}
+
+struct TcPlan {
+  int m_tile, split_k, kb_per_split;
+};
+
+static TcPlan tc_plan(int M, int K, int N) {
+  TcPlan pl;
+  int mt = g_tc_tuning.m_tile;
+  if (mt != 16 && mt != 32 && mt != 64 && mt != 128 && mt != 256) {
+    mt = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  }
+  pl.m_tile = mt;
+  const int kblocks = K / 64;
+  const int tiles = ((N + 127) / 128) * ((M + mt - 1) / mt);
+  int ks = 1;
+  if (g_tc_tuning.split_k > 0) {
+    ks = g_tc_tuning.split_k;
+  } else if (tiles < 148) {
+    ks = (148 + tiles - 1) / tiles;          // aim for one wave of CTAs
+    while (ks > 1 && kblocks / ks < 4) --ks;  // keep at least four K blocks per CTA
+  }
+  if (ks > kblocks) ks = kblocks;
+  if (ks > 32) ks = 32;
+  pl.kb_per_split = (kblocks + ks - 1) / ks;
+  pl.split_k = (kblocks + pl.kb_per_split - 1) / pl.kb_per_split;
+  return pl;
+}
+
+bool tc_supported(const Problem& p, int bits) {
+  (void)bits;
+  return encode_fn() != nullptr && p.K % 64 == 0 && p.N % 64 == 0 && p.g % 64 == 0;
+}
+
+size_t tc_workspace_bytes(int64_t M, int64_t K, int64_t N) {
+  const TcPlan pl = tc_plan(int(M), int(K), int(N));
+  return pl.split_k > 1 ? size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.split_k) * M * N * sizeof(float) : 0;
+}
+
+template <class A, int BITS, int MT, bool TS, int ZK>
+static int launch_cfg(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& prm, dim3 grid, cudaStream_t stream) {
+  using Cfg = TcCfg<MT, BITS, TS>;
+  auto kern = tc_kernel<A, BITS, MT, TS, ZK>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    CB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(mx, mw, prm);
+  CB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <class A, int BITS, int MT, bool TS>
+static int launch_zk(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& prm, dim3 grid, cudaStream_t stream) {
+  switch (prm.p.zp_kind) {
+    case CB200_ZP_NONE: return launch_cfg<A, BITS, MT, TS, CB200_ZP_NONE>(mx, mw, prm, grid, stream);
+    case CB200_ZP_I32: return launch_cfg<A, BITS, MT, TS, CB200_ZP_I32>(mx, mw, prm, grid, stream);
+    case CB200_ZP_U8: return launch_cfg<A, BITS, MT, TS, CB200_ZP_U8>(mx, mw, prm, grid, stream);
+    default: return launch_cfg<A, BITS, MT, TS, CB200_ZP_ACT>(mx, mw, prm, grid, stream);
+  }
+}
+
+template <class A, int BITS, bool TS>
+static int launch_mt(int mt, const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& prm, dim3 grid, cudaStream_t stream) {
+  switch (mt) {
+    case 16: return launch_zk<A, BITS, 16, TS>(mx, mw, prm, grid, stream);
+    case 32: return launch_zk<A, BITS, 32, TS>(mx, mw, prm, grid, stream);
+    case 64: return launch_zk<A, BITS, 64, TS>(mx, mw, prm, grid, stream);
+    case 128: return launch_zk<A, BITS, 128, TS>(mx, mw, prm, grid, stream);
+    default: return launch_zk<A, BITS, 256, TS>(mx, mw, prm, grid, stream);
+  }
+}
+
+int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, size_t ws_bytes, cudaStream_t stream,
+              int* launches) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return CB200_ERR_DEVICE;
+  }
+  const TcPlan pl = tc_plan(p.M, p.K, p.N);
+  const int mt = pl.m_tile;
+  const int pf = 32 / bits;
+
+  // x: [M, K] row-major -> dims {K, M}, box {64, m_tile}, 128-byte swizzle; rows beyond M are zero-filled by TMA
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[2] = {cuuint64_t(p.K), cuuint64_t(p.M)};
+    const cuuint64_t strides[1] = {cuuint64_t(p.K) * 2};
+    const cuuint32_t box[2] = {64, cuuint32_t(mt)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&mx, act_dtype == CB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                           const_cast<void*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(x) failed: %d", int(r));
+      return CB200_ERR_ARG;
+    }
+  }
+  // packed W: [K/pf, N] int32 -> dims {N, K/pf}, box {128, 64/pf}, no swizzle; columns beyond N zero-filled
+  {
+    const cuuint64_t dims[2] = {cuuint64_t(p.N), cuuint64_t(p.K / pf)};
+    const cuuint64_t strides[1] = {cuuint64_t(p.N) * 4};
+    const cuuint32_t box[2] = {128, cuuint32_t(64 / pf)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<uint32_t*>(p.wq), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(w_q_packed) failed: %d", int(r));
+      return CB200_ERR_ARG;
+    }
+  }
+
+  TcParams prm;
+  prm.p = p;
+  prm.kblocks_total = p.K / 64;
+  prm.kb_per_split = pl.kb_per_split;
+  prm.ws_partial = nullptr;
+  if (pl.split_k > 1) {
+    const size_t need = size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.split_k) * p.M * p.N * sizeof(float);
+    if (!ws || ws_bytes < need) {
+      set_error("tcgen05 split-K=%d needs %zu workspace bytes, got %zu", pl.split_k, need, ws_bytes);
+      return CB200_ERR_WORKSPACE;
+    }
+    prm.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES);
+  }
+  dim3 grid((p.N + 127) / 128, (p.M + mt - 1) / mt, pl.split_k);
+  const bool ts = variant != CB200_TC_SS;
+  int rc;
+  if (act_dtype == CB200_F16) {
+    rc = bits == 4 ? (ts ? launch_mt<__half, 4, true>(mt, mx, mw, prm, grid, stream) : launch_mt<__half, 4, false>(mt, mx, mw, prm, grid, stream))
+                   : (ts ? launch_mt<__half, 8, true>(mt, mx, mw, prm, grid, stream) : launch_mt<__half, 8, false>(mt, mx, mw, prm, grid, stream));
+  } else {
+    rc = bits == 4 ? (ts ? launch_mt<__nv_bfloat16, 4, true>(mt, mx, mw, prm, grid, stream)
+                         : launch_mt<__nv_bfloat16, 4, false>(mt, mx, mw, prm, grid, stream))
+                   : (ts ? launch_mt<__nv_bfloat16, 8, true>(mt, mx, mw, prm, grid, stream)
+                         : launch_mt<__nv_bfloat16, 8, false>(mt, mx, mw, prm, grid, stream));
+  }
+  if (rc) return rc;
+  if (launches) ++*launches;
+  if (pl.split_k > 1) {
+    const int64_t total = int64_t(p.M) * p.N;
+    int blocks = int((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(prm.ws_partial, p.out, total, pl.split_k, p.out_dtype);
+    CB200_CUDA_CHECK(cudaGetLastError());
+    if (launches) ++*launches;
+  }
+  return 0;
+}
+
 }  // namespace cb200

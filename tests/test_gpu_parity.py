@@ -20,11 +20,10 @@ from helpers import ATOL, DTYPES, RTOL, assert_gemm_close, bits, golden_id, gold
 pytestmark = pytest.mark.gpu
 INDEX = golden_index()
 
-ALL_VARIANTS = [_lib.DECODE_MMA]
+ALL_VARIANTS = [_lib.DECODE_MMA, _lib.TC_SS, _lib.TC_TS]
 
 
 def _variants_for(m: int) -> list[int]:
-    lib = _lib.load()  # noqa: F841
     return ALL_VARIANTS
 
 
@@ -167,17 +166,84 @@ def test_split_k_workspace_is_reusable_and_deterministic():
     assert_gemm_close(first, want)
 
 
-@pytest.mark.parametrize("vec", [2, 4])
-@pytest.mark.parametrize("warps", [(1, 16), (2, 8), (4, 4), (1, 8), (2, 2)])
-def test_decode_tilings(vec, warps):
+@pytest.mark.parametrize("scale_mode", [1, 2], ids=["scale_in_loop", "scale_after"])
+@pytest.mark.parametrize("units_per_warp", [0, 1, 2, 3, 5, 64])
+def test_decode_tilings(scale_mode, units_per_warp):
+    """Stream-K ranges that cut column blocks at every possible place, both scaling modes."""
     lib = _lib.load()
     try:
-        lib.cb200_set_decode_tuning(warps[0], warps[1], 0, vec)
+        lib.cb200_set_decode_tuning(scale_mode, 0, units_per_warp, 0)
         for m in (1, 12):
             _run_case(m, 2048, 512, "uint4", 128, torch.float16, True, variant=_lib.DECODE_MMA)
             _run_case(m, 1024, 256, "uint8b128", 128, torch.bfloat16, True, variant=_lib.DECODE_MMA)
+            _run_case(m, 1024, 256, "uint4b8", 64, torch.bfloat16, False, variant=_lib.DECODE_MMA)
     finally:
         lib.cb200_set_decode_tuning(0, 0, 0, 0)
+
+
+def test_decode_scale_in_loop_is_the_reference_arithmetic():
+    """With the scale applied per weight (mode 1) a one-hot x reproduces the dequantised row bit for bit."""
+    lib = _lib.load()
+    p = oracle.make_problem(1, 1024, 256, "uint4", 128, torch.float16, True, seed=9)
+    _, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    x = torch.zeros((1, 1024), device="cuda", dtype=torch.float16)
+    x[0, 517] = 1.0
+    try:
+        lib.cb200_set_decode_tuning(1, 0, 0, 0)
+        out = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.DECODE_MMA)
+    finally:
+        lib.cb200_set_decode_tuning(0, 0, 0, 0)
+    assert torch.equal(bits(out[0]), bits(p.w_ref[517]))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tcgen05 path
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [_lib.TC_SS, _lib.TC_TS], ids=["ss", "ts"])
+@pytest.mark.parametrize("m", [1, 16, 17, 33, 64, 100, 128, 129, 256, 300, 512])
+def test_tc_m_sweep(variant, m):
+    _run_case(m, 512, 256, "uint4", 128, torch.float16, True, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [_lib.TC_SS, _lib.TC_TS], ids=["ss", "ts"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("wname", ["uint4", "uint4b8", "uint8", "uint8b128"])
+@pytest.mark.parametrize("zp", [True, False], ids=["zp", "sym"])
+def test_tc_formats(variant, dtype, wname, zp):
+    _run_case(192, 1024, 384, wname, 128, dtype, zp, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [_lib.TC_SS, _lib.TC_TS], ids=["ss", "ts"])
+@pytest.mark.parametrize("g", [64, 256, -1])
+def test_tc_group_sizes_and_split_k(variant, g):
+    lib = _lib.load()
+    _run_case(48, 2048, 256, "uint4b8", g, torch.bfloat16, True, variant=variant)
+    try:
+        lib.cb200_set_tc_tuning(0, 3)
+        _run_case(48, 2048, 256, "uint4", g, torch.float16, True, variant=variant)
+        lib.cb200_set_tc_tuning(64, 0)
+        _run_case(200, 1024, 320, "uint8", g, torch.float16, True, variant=variant, zp_as=torch.uint8)
+    finally:
+        lib.cb200_set_tc_tuning(0, 0)
+
+
+@pytest.mark.parametrize("variant", [_lib.TC_SS, _lib.TC_TS], ids=["ss", "ts"])
+def test_tc_one_hot_rows_reproduce_dequantised_weights(variant):
+    """x = one-hot rows => out == W rows bit for bit: the tcgen05 path feeds the SAME dequant bits to the MMA."""
+    p = oracle.make_problem(1, 1024, 256, "uint4", 128, torch.float16, True, seed=11)
+    _, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    rows = [0, 1, 63, 64, 65, 127, 128, 511, 512, 1023] + list(range(300, 330))
+    x = torch.zeros((len(rows), 1024), device="cuda", dtype=torch.float16)
+    for i, r in enumerate(rows):
+        x[i, r] = 1.0
+    out = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=variant)
+    assert torch.equal(bits(out), bits(p.w_ref[rows]))
+
+
+@pytest.mark.parametrize("variant", [_lib.TC_SS, _lib.TC_TS], ids=["ss", "ts"])
+def test_tc_prefill_shape(variant):
+    """A slice of BASELINE config 3 (M=4096 would take the CPU oracle too long): M=512, K=4096, N=1024."""
+    _run_case(512, 4096, 1024, "uint4", 128, torch.float16, True, variant=variant)
 
 
 # ------------------------------------------------------------------------------------------------------------
