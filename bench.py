@@ -232,9 +232,15 @@ def run_gpu_arm(args) -> None:
     gen = torch.Generator(device=dev).manual_seed(7)
     xs = [torch.randn((M, k), generator=gen, device=dev, dtype=torch.float16) for _, k, _ in PROJECTIONS]
     outs = [[torch.empty((M, n), device=dev, dtype=torch.float16) for _, _, n in PROJECTIONS] for _ in range(LAYERS)]
-    gathered = None
+    sharded = None
     if world > 1:
-        gathered = [torch.empty((world, M, n), device=dev, dtype=torch.float16) for _, _, n in PROJECTIONS]
+        # every rank holds an equally sized column shard of a world-times wider layer (weak scaling)
+        from conch_b200.sharded import ShardedMixedPrecisionLinear
+
+        sharded = [
+            [ShardedMixedPrecisionLinear(*weights[layer][pi], BITS, BIAS, GROUP, already_sharded=True) for pi in range(len(PROJECTIONS))]
+            for layer in range(LAYERS)
+        ]
 
     launches_per_step = 0
 
@@ -243,11 +249,12 @@ def run_gpu_arm(args) -> None:
         for layer in range(LAYERS):
             for pi in range(len(PROJECTIONS)):
                 packed, w_s, w_zp = weights[layer][pi]
-                mixed_precision_gemm(xs[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=outs[layer][pi])
+                if world > 1:
+                    sharded[layer][pi].gathered(xs[pi], out=outs[layer][pi])  # GEMM on the shard + NCCL all-gather
+                else:
+                    mixed_precision_gemm(xs[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=outs[layer][pi])
                 if count:
                     launches_per_step += lib.cb200_last_launch_count()
-                if world > 1:
-                    dist.all_gather_into_tensor(gathered[pi], outs[layer][pi])
 
     def barrier():
         if world > 1:
@@ -313,9 +320,10 @@ def run_gpu_arm(args) -> None:
         for layer in range(LAYERS):
             for pi in range(len(PROJECTIONS)):
                 packed, w_s, w_zp = weights[layer][pi]
-                mixed_precision_gemm(x_dev[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=out_views[layer][pi].view(M, -1))
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered[pi], out_views[layer][pi].view(M, -1))
+                    sharded[layer][pi].gathered(x_dev[pi], out=out_views[layer][pi].view(M, -1))
+                else:
+                    mixed_precision_gemm(x_dev[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=out_views[layer][pi].view(M, -1))
         out_host.copy_(out_dev, non_blocking=True)
 
     e2e_steps = max(3, min(args.steps, 50))

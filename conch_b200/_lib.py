@@ -31,6 +31,7 @@ EXPORTS = (
     "cb200_dequantize",
     "cb200_set_decode_tuning",
     "cb200_set_tc_tuning",
+    "cb200_set_pdl",
 )
 
 _lock = threading.Lock()
@@ -86,6 +87,8 @@ def load() -> ctypes.CDLL:
         lib.cb200_set_decode_tuning.argtypes = [c_int, c_int, c_int, c_int]
         lib.cb200_set_tc_tuning.restype = None
         lib.cb200_set_tc_tuning.argtypes = [c_int, c_int]
+        lib.cb200_set_pdl.restype = None
+        lib.cb200_set_pdl.argtypes = [c_int]
         _lib = lib
     return _lib
 

@@ -52,6 +52,7 @@ struct DecodeTuning {
   int warps_n, warps_k, split_k, vec_words;
 };
 extern DecodeTuning g_decode_tuning;
+extern int g_decode_pdl;
 struct TcTuning {
   int m_tile, split_k;
 };

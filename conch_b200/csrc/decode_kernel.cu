@@ -1,28 +1,38 @@
-// Decode-regime kernel (M <= 16 per pass): stream-K skinny GEMM, HBM-bound.
+// Decode-regime kernel (M <= 16 per pass): split-K skinny GEMM, HBM-bound.
 //
 // Replaces the reference's single 128x64x64 Triton tile (conch/kernels/quantization/gemm.py:136-145, 491-494),
 // which at M=1 launches N/64 CTAs with no split-K.  Design (B200):
-//   * work = (32-column block) x (batch of U steps, one step = 4 packed rows) units, flattened column-major and cut
-//     into W equal contiguous ranges, one per WARP (stream-K at warp granularity).  W is chosen so that the whole grid
-//     is one co-resident wave; warps are completely independent (no shared memory, no __syncthreads);
-//   * the packed weights are the only large stream: every lane issues 128-bit coalesced, read-once cp.async.cg copies
-//     (L2 -> shared, bypassing L1 and the register file) into a private per-warp ring LOOK batches ahead of the one
-//     being consumed, so ~100 KB per SM is in flight regardless of register pressure; a lane only ever reads back
-//     its own 16 bytes, so the ring needs no barrier, just cp.async.wait_group;
-//   * nibbles are unpacked and the exact integer (q - bias - zp) is formed in registers with the magic-number tricks
-//     of dequant.cuh; with SA=false the scale multiply is done per weight (dequant_word(): bit-identical W to
-//     the dequant kernel and the reference's w_ref), with SA=true the per-group scale is applied once to the
-//     fp32 group sum instead (sum_k x_k (q_k - zp) is exact in the tensor core, so this differs from the reference
-//     only by NOT rounding each W to fp16/bf16 -- well inside the 1e-2 tolerance, and ~25% fewer instructions on a
-//     kernel that is issue-bound right at the HBM roofline);
+//   * one WARP owns one (32-column block) x (1/S of K) slab; S is a divisor of the batches per column chosen so that the
+//     whole grid is one co-resident wave.  Warps are completely independent: no __syncthreads, no shared state;
+//   * the packed weights are the only large stream: every lane keeps a rotating window of 2*U (= 8) 128-bit read-once
+//     loads (ld.global.nc, L1 no-allocate) in flight -- the register that held step j is re-loaded with step j + 2U as
+//     soon as it has been read -- so with ~24 resident warps per SM about 100 KB per SM is outstanding, which is what it
+//     takes to approach the HBM peak (measured: benchmarks/micro/stream_pattern.cu).  cp.async was measured and
+//     rejected: with 4 row segments per instruction LDGSTS serialises into 32 shared-memory wavefronts
+//     (benchmarks/micro/decode_steps.cu).  The activations (16 B per lane per step) come through L1, prefetched one step
+//     ahead; scales / zero-points are prefetched one group ahead in registers and several groups ahead into L2.
+//     All cursors are linear pointer increments;
+//   * FUSED=false: nibbles are unpacked and W = (q - bias - zp) * s is formed per weight with dequant_word() -- the
+//     same bits as the dequant kernel and the reference's w_ref -- before the MMA;
+//   * FUSED=true (opt-in, cb200_set_decode_tuning(2,..): fewer instructions per weight but, as compiled today, 128
+//     registers per thread and lower occupancy -- measured slower than FUSED=false, kept for round 2): the
+//     magic-number operand itself, 0x6400|q = 1024 + q (fp16) or 0x4300|q = 128 + q (bf16), goes into the MMA, so a word
+//     costs 1 shift + 4 lop3 and NO floating-point op.  One extra MMA per step with an all-ones A operand yields
+//     X = sum_k x_k in the same fragment layout, and at each group boundary
+//         acc += s[n] * ( D[n,m] - MAGIC * X[m] - (bias + zp[n]) * X[m] )
+//     (fp16 int4 keeps the x16-scaled odd nibbles in a second accumulator: D = D_even + D_odd / 16, offsets 1024 / 64).
+//     sum_k x_k q_k is exact in the tensor core; the result differs from the reference only by not rounding each W to
+//     fp16/bf16 and by fp32 cancellation of the MAGIC * X term (~1e-5 relative), far inside the 1e-2 tolerance;
 //   * the dot product runs on the tensor pipe as mma.sync.m16n8k16 with the WEIGHTS as the 16-row operand (swap-AB) and
 //     x^T as the 8-column operand; the four lanes of a quad hold four different packed rows, so the K-reduction
-//     across lanes happens inside the MMA, fp32 accumulate;
-//   * x is tiny and shared by every warp of the SM: read through L1 (16 B per lane per step) and permuted in registers
-//     to the nibble order the cheap `lop3` extraction produces ((k0,k4),(k1,k5),(k2,k6),(k3,k7));
-//   * a warp whose range covers a whole column block stores the result directly; otherwise it writes an fp32 partial,
-//     bumps the block's arrival counter, and the last arriver sums the partials in slot order (deterministic,
-//     self-resetting counters: no memset, no second launch).
+//     across lanes happens inside the MMA, fp32 accumulate; x is permuted in registers to the nibble order the cheap
+//     `lop3` extraction produces ((k0,k4),(k1,k5),(k2,k6),(k3,k7));
+//   * S == 1: the warp stores its result directly.  S > 1: it writes an fp32 partial, bumps the column block's arrival
+//     counter, and the last arriver sums the S partials in slab order (deterministic, self-resetting counters: no
+//     memset, no second launch);
+//   * programmatic dependent launch (opt-in, cb200_set_pdl): the weight / metadata prefetch is issued BEFORE
+//     griddepcontrol.wait, so launch latency, prologue and the first DRAM round trip overlap the previous kernel's tail;
+//     x, the output and the workspace are only touched after the wait.
 #include "common.cuh"
 #include "dequant.cuh"
 
@@ -32,11 +42,11 @@ DecodeTuning g_decode_tuning = {0, 0, 0, 0};
 
 struct DecodeGeom {
   int m_rows;         // rows of x in this pass (<= 16)
-  int units_per_col;  // B: batches per column block = K / (U * STEP_K)
-  int q, r;           // warp w owns q + (w < r) consecutive units starting at w*q + min(w, r)
-  int total_warps;    // W
-  int col_blocks;     // N / 32
-  int slots_max;      // partial slots reserved per column block
+  int splits;         // S: warps sharing one column block (split-K)
+  int units_per_warp; // batches per warp = K / (U * STEP_K * S)
+  int total_warps;    // (N / 32) * S
+  int bpg;            // batches per scale group (g / (U * STEP_K))
+  int pdl;            // launched with programmatic stream serialization
 };
 
 template <class A>
@@ -55,277 +65,329 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const float (&c)[4], uin
   }
 }
 
-constexpr int kDecodeRingSteps = 12;  // weight ring depth per warp, in steps (512 B each): 6 KB per warp
-
-// unit index -> owning warp (inverse of the range function above)
-__device__ __forceinline__ int unit_owner(int u, int q, int r) {
-  const int head = r * (q + 1);
-  return u < head ? u / (q + 1) : r + (u - head) / q;
-}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // A: activation type, BITS: 4|8, MT: 8-row m tiles (1: M<=8, 2: M<=16), U: steps per batch (group boundaries fall on
-// batch boundaries), ZK: cb200_zp_kind (compile time), SA: apply the group scale after the group's dot product.
-template <class A, int BITS, int MT, int U, int ZK, bool SA>
-__global__ void __launch_bounds__(128, MT == 1 ? 6 : 4)
-    decode_kernel(Problem p, DecodeGeom geo, float* __restrict__ ws_partial, unsigned int* __restrict__ ws_counter) {
+// batch boundaries), ZK: cb200_zp_kind (compile time), FUSED: feed magic-number operands to the MMA (see above).
+template <class A, int BITS, int MT, int U, int ZK, bool FUSED>
+__global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
+    decode_kernel(const Problem p, const DecodeGeom geo, float* __restrict__ ws_partial, unsigned int* __restrict__ ws_counter) {
   constexpr int PF = 32 / BITS;     // k per packed word
-  constexpr int STEP_K = 4 * PF;    // k per step (4 packed rows, one per lane of a quad)
   constexpr int VEC = 4;            // packed words per lane per load (128-bit)
   constexpr int NT = VEC / 2;       // 16-column MMA tiles per warp
   constexpr int CW = 8 * VEC;       // columns per warp
   constexpr int PAIRS = 16 / BITS;  // pair registers per word
+  constexpr int WIN = 2 * U;        // weight loads in flight per lane (steps)
   constexpr Order ORD = Order::Lop;
   constexpr bool FZP = ZK == CB200_ZP_ACT;
-  constexpr int LOOK = kDecodeRingSteps / U - 1;  // batches in flight ahead of the one being consumed
-  constexpr int SLOTS = LOOK + 1;
 
-  extern __shared__ __align__(16) unsigned char ring_raw[];  // [warps][SLOTS][U][32 lanes][16 B]
+  if (geo.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the next kernel's CTAs queue up
 
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (w >= geo.total_warps) return;
   const int g8 = lane >> 2, tig = lane & 3;
   const int M = geo.m_rows;
   const int N = p.N;
-  const int B = geo.units_per_col;
+  const int S = geo.splits;
+  const int cb = w / S;               // column block
+  const int si = w - cb * S;          // slab index inside the column block
+  const int nunits = geo.units_per_warp;
+  const int nsteps = nunits * U;
+  const int b0 = si * nunits;         // first batch of this warp
+  const int bpg = geo.bpg;
+  const int col = cb * CW + VEC * g8; // first of this lane's four weight columns
+  const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
 
-  const int n_units = geo.q + (w < geo.r ? 1 : 0);
-  const int u0 = w * geo.q + min(w, geo.r);
-  int cb = u0 / B;       // column block
-  int b = u0 - cb * B;   // batch inside the column block
-  const int lane_col = VEC * g8;
-
-  // ---- weight ring: get LOOK batches in flight before anything else ------------------------------------------------
-  const size_t step_stride = size_t(4) * N;      // words between consecutive steps of one lane
-  const size_t unit_stride = step_stride * U;    // words between consecutive batches
-  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(ring_raw)) +
-                        (threadIdx.x >> 5) * (SLOTS * U * 512) + lane * 16;
-  // issue cursor: runs LOOK units ahead of the consume cursor (cb, b)
-  int icb = cb, ib = b;
-  const uint32_t* iwp = p.wq + (size_t(b) * (U * 4) + tig) * N + cb * CW + lane_col;
-  auto issue_unit = [&](int slot) {
-    const uint32_t dst = ring + slot * (U * 512);
+  // ---- weight window: WIN loads in flight before anything else (weights are static: legal before griddepcontrol.wait) ----
+  const char* wp = reinterpret_cast<const char*>(p.wq + (size_t(b0) * (U * 4) + tig) * N + col);
+  const size_t step_bytes = size_t(16) * N;  // 4 packed rows
+  uint4 win[WIN];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * 512), "l"(iwp + u * step_stride) : "memory");
-    }
-    ++ib;
-    iwp += unit_stride;
-    if (ib == B) {
-      ib = 0;
-      ++icb;
-      iwp = p.wq + size_t(tig) * N + icb * CW + lane_col;
+  for (int j = 0; j < WIN; ++j) {
+    win[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (j < nsteps) win[j] = ldg_stream_v4(wp + j * step_bytes);
+  }
+  wp += WIN * step_bytes;  // next load of slot j: wp + j * step_bytes
+
+  // ---- scales / zero-points: raw values of the NEXT group live in registers, converted when that group starts ----------
+  const int g0 = b0 / bpg;  // a slab either covers whole groups or lies inside one group
+  const int ngroups_mine = (nunits + bpg - 1) / bpg;
+  const A* sptr = reinterpret_cast<const A*>(p.s) + size_t(g0) * N + col;
+  const char* zptr = nullptr;
+  size_t z_row_bytes = 0;
+  if (zp_per_group) {
+    const size_t zes = ZK == CB200_ZP_I32 ? 4 : ZK == CB200_ZP_U8 ? 1 : 2;
+    zptr = reinterpret_cast<const char*>(p.zp) + (size_t(g0) * N + col) * zes;
+    z_row_bytes = size_t(N) * zes;
+  }
+  uint2 raw_s = make_uint2(0u, 0u);
+  uint4 raw_z = make_uint4(0u, 0u, 0u, 0u);
+  auto fetch_meta = [&]() {  // loads only: nothing here may depend on the loaded values
+    raw_s = __ldg(reinterpret_cast<const uint2*>(sptr));
+    sptr += N;
+    if (zp_per_group) {
+      if constexpr (ZK == CB200_ZP_I32) raw_z = __ldg(reinterpret_cast<const uint4*>(zptr));
+      if constexpr (ZK == CB200_ZP_U8) raw_z.x = __ldg(reinterpret_cast<const uint32_t*>(zptr));
+      if constexpr (ZK == CB200_ZP_ACT) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(zptr));
+        raw_z.x = t.x;
+        raw_z.y = t.y;
+      }
+      zptr += z_row_bytes;
     }
   };
+  fetch_meta();
+  int groups_fetched = 1;
+  if (tig == 0) {  // pull the next few groups' metadata rows into L2 (one lane per distinct address)
 #pragma unroll
-  for (int j = 0; j < LOOK; ++j) {
-    if (j < n_units) issue_unit(j);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-
-  // ---- per-group constants ---------------------------------------------------------------------------------------
-  const int bpg = p.g / (U * STEP_K);  // batches per group (host guarantees divisibility)
-  const int ngrp = p.K / p.g;
-  A raw_s[VEC];
-  float raw_z[VEC];
-  A raw_zf[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    raw_z[j] = 0.f;
-    raw_zf[j] = A(0.f);
-  }
-  if (ZK != CB200_ZP_NONE && p.zp_scalar) {  // one zero-point for the whole matrix: fetch it once
-    float z = 0.f;
-    A zf = A(0.f);
-    if constexpr (ZK == CB200_ZP_I32) z = float(__ldg(reinterpret_cast<const int32_t*>(p.zp)));
-    if constexpr (ZK == CB200_ZP_U8) z = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp)));
-    if constexpr (ZK == CB200_ZP_ACT) zf = *reinterpret_cast<const A*>(p.zp);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      raw_z[j] = z;
-      raw_zf[j] = zf;
-    }
-  }
-  const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
-  // meta = element index of (group, first column of this lane) in the [K/g, N] scale / zero-point matrices
-  auto fetch_meta = [&](uint32_t meta) {
-    *reinterpret_cast<uint2*>(raw_s) = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const A*>(p.s) + meta));
-    if (zp_per_group) {
-      if constexpr (ZK == CB200_ZP_I32) {
-        const int4 z = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(p.zp) + meta));
-        raw_z[0] = float(z.x); raw_z[1] = float(z.y); raw_z[2] = float(z.z); raw_z[3] = float(z.w);
-      } else if constexpr (ZK == CB200_ZP_U8) {
-        const uint32_t z = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p.zp) + meta));
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) raw_z[j] = float((z >> (8 * j)) & 0xffu);
-      } else if constexpr (ZK == CB200_ZP_ACT) {
-        *reinterpret_cast<uint2*>(raw_zf) = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const A*>(p.zp) + meta));
+    for (int j = 0; j < 3; ++j) {
+      if (j + 1 < ngroups_mine) {
+        prefetch_l2(sptr + size_t(j) * N);
+        if (zp_per_group) prefetch_l2(zptr + j * z_row_bytes);
       }
     }
-  };
-  int grp = b / bpg;
-  int batches_left = bpg - (b - grp * bpg);  // batches until the current group ends
-  bool refresh = true;
-  uint32_t meta = uint32_t(grp) * N + cb * CW + lane_col;
-  fetch_meta(meta);
-  ColQ cq[VEC];
-  float sc[VEC];  // SA: group scales as fp32
-  const float fbias = float(p.bias);
+  }
 
-  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
-  float acc[NT][MT][4];   // running sum of this column segment
-  float accg[NT][MT][4];  // SA: sum of the current group, still unscaled
-#pragma unroll
-  for (int t = 0; t < NT; ++t)
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[t][mt][i] = accg[t][mt][i] = 0.f;
-  bool group_open = false;  // SA: accg holds a partial group
+  if (geo.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // x / out / workspace belong to the stream order
 
-  // x rows this lane feeds to the MMA B operand (column g8 of the 8-wide m tile); xp follows the current batch
-  const A* xp[MT];
+  // ---- activations: one step prefetched ahead through L1 ---------------------------------------------------------------------
   bool m_ok[MT];
-  uint32_t xb[MT][PAIRS];
+  const A* xp[MT];
+  uint4 xnext[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int m = mt * 8 + g8;
     m_ok[mt] = m < M;
-    xp[mt] = reinterpret_cast<const A*>(p.x) + size_t(m_ok[mt] ? m : 0) * p.K + tig * PF + size_t(b) * (U * 4 * PF);
-#pragma unroll
-    for (int i = 0; i < PAIRS; ++i) xb[mt][i] = 0u;
+    xp[mt] = reinterpret_cast<const A*>(p.x) + size_t(m_ok[mt] ? m : 0) * p.K + tig * PF + size_t(b0) * (U * 4 * PF);
+    xnext[mt] = make_uint4(0u, 0u, 0u, 0u);
+    if (m_ok[mt]) {
+      if constexpr (BITS == 4) {
+        xnext[mt] = __ldg(reinterpret_cast<const uint4*>(xp[mt]));
+      } else {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(xp[mt]));
+        xnext[mt].x = t.x;
+        xnext[mt].y = t.y;
+      }
+    }
+    xp[mt] += 4 * PF;
   }
 
-  auto close_group = [&]() {  // SA: acc += scale (per weight column) * group sum
-    // rows of the C fragment are weight columns: c0,c1 <- column 2t, c2,c3 <- column 2t+1 of this lane
+  // ---- consume-side state ---------------------------------------------------------------------------------------------------
+  float zscalar = 0.f;
+  A zfscalar = A(0.f);
+  if (ZK != CB200_ZP_NONE && p.zp_scalar) {  // one zero-point for the whole matrix: fetch it once
+    if constexpr (ZK == CB200_ZP_I32) zscalar = float(__ldg(reinterpret_cast<const int32_t*>(p.zp)));
+    if constexpr (ZK == CB200_ZP_U8) zscalar = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp)));
+    if constexpr (ZK == CB200_ZP_ACT) zfscalar = *reinterpret_cast<const A*>(p.zp);
+  }
+  int batches_left = bpg - (b0 % bpg);  // batches until the current group ends
+  bool refresh = true;
+  const float fbias = float(p.bias);
+  // FUSED layout: fp16/int4 has two operand kinds per word (plain and x16 nibbles) -> two accumulators
+  constexpr bool TWO = FUSED && std::is_same<A, __half>::value && BITS == 4;
+  constexpr float MAGIC = std::is_same<A, __half>::value ? 1024.f : 128.f;
+  constexpr uint32_t ONES = std::is_same<A, __half>::value ? 0x3C003C00u : 0x3F803F80u;  // (1.0, 1.0)
+  constexpr int NACC = TWO ? 2 : 1;
+
+  ColQ cq[VEC];     // !FUSED: per-column dequant constants
+  float sc[VEC];    // FUSED: group scales as fp32
+  float zb[VEC];    // FUSED: bias + zero-point per column
+
+  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[NT][MT][4];          // running (scaled) sum of this warp's slab
+  float accg[NACC][NT][MT][4];   // FUSED: raw sums of the current group (even / odd operand kinds)
+  float xs[NACC][MT][4];         // FUSED: sum_k x_k of the current group from the all-ones MMA (rows are identical)
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        acc[t][mt][0] = fmaf(accg[t][mt][0], sc[2 * t], acc[t][mt][0]);
-        acc[t][mt][1] = fmaf(accg[t][mt][1], sc[2 * t], acc[t][mt][1]);
-        acc[t][mt][2] = fmaf(accg[t][mt][2], sc[2 * t + 1], acc[t][mt][2]);
-        acc[t][mt][3] = fmaf(accg[t][mt][3], sc[2 * t + 1], acc[t][mt][3]);
+      for (int i = 0; i < 4; ++i) {
+        acc[t][mt][i] = 0.f;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) accg[a][t][mt][i] = 0.f;
       }
-  };
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xs[a][mt][i] = 0.f;
+  }
+  bool group_open = false;  // FUSED: accg / xs hold a partial group
 
-  // ---- flush one finished (or cut) column segment ------------------------------------------------------------------
-  auto flush = [&](int cbi) {
-    const int first_w = unit_owner(cbi * B, geo.q, geo.r);
-    const int last_w = unit_owner(cbi * B + B - 1, geo.q, geo.r);
-    const int ncol0 = cbi * CW + lane_col;
-    if (first_w == last_w) {  // this warp saw the whole K range: store directly
+  auto close_group = [&]() {  // FUSED: acc += s[n] * (D - offset * X - zb[n] * X)
+    // C fragment: c0,c1 <- weight column 2t (m = 2tig, 2tig+1); c2,c3 <- weight column 2t+1 of this lane
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float off[2], xsum[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if constexpr (TWO) {
+          off[j] = fmaf(1024.f, xs[0][mt][j], 64.f * xs[1][mt][j]);
+          xsum[j] = xs[0][mt][j] + xs[1][mt][j];
+        } else {
+          off[j] = MAGIC * xs[0][mt][j];
+          xsum[j] = xs[0][mt][j];
+        }
+      }
 #pragma unroll
       for (int t = 0; t < NT; ++t)
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int m = mt * 8 + 2 * tig;
-          const int n = ncol0 + 2 * t;
-          if (m < M) {
-            store_out<A>(p.out, p.out_dtype, size_t(m) * N + n, acc[t][mt][0]);
-            store_out<A>(p.out, p.out_dtype, size_t(m) * N + n + 1, acc[t][mt][2]);
-          }
-          if (m + 1 < M) {
-            store_out<A>(p.out, p.out_dtype, size_t(m + 1) * N + n, acc[t][mt][1]);
-            store_out<A>(p.out, p.out_dtype, size_t(m + 1) * N + n + 1, acc[t][mt][3]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          const int c = 2 * t + (i >> 1), j = i & 1;
+          float d = accg[0][t][mt][i];
+          if constexpr (TWO) d = fmaf(accg[1][t][mt][i], 0.0625f, d);
+          d -= off[j];
+          d = fmaf(-zb[c], xsum[j], d);
+          acc[t][mt][i] = fmaf(sc[c], d, acc[t][mt][i]);
         }
-      return;
     }
-    const int contributors = last_w - first_w + 1;
-    float* mine = ws_partial + (size_t(cbi) * geo.slots_max + (w - first_w)) * (M * CW);
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const int m = mt * 8 + 2 * tig;
-        const int lc = lane_col + 2 * t;
-        if (m < M) {
-          __stcg(mine + m * CW + lc, acc[t][mt][0]);
-          __stcg(mine + m * CW + lc + 1, acc[t][mt][2]);
-        }
-        if (m + 1 < M) {
-          __stcg(mine + (m + 1) * CW + lc, acc[t][mt][1]);
-          __stcg(mine + (m + 1) * CW + lc + 1, acc[t][mt][3]);
-        }
-      }
-    __threadfence();
-    __syncwarp();
-    unsigned prev = 0;
-    if (lane == 0) prev = atomicAdd(ws_counter + cbi, 1u);
-    prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev != unsigned(contributors - 1)) return;
-    __threadfence();  // last arriver: every other contributor's partial is visible now
-    const float* base = ws_partial + size_t(cbi) * geo.slots_max * (M * CW);
-    for (int e = lane; e < M * CW; e += 32) {
-      float v = 0.f;
-      for (int s = 0; s < contributors; ++s) v += __ldcg(base + size_t(s) * (M * CW) + e);
-      const int m = e / CW, lc = e - m * CW;
-      store_out<A>(p.out, p.out_dtype, size_t(m) * N + cbi * CW + lc, v);
-    }
-    if (lane == 0) ws_counter[cbi] = 0u;  // leave the counter clean for the next launch
   };
 
-  // ---- one unit: U steps of dequant + MMA on the weights already in registers ------------------------------------------
-  auto process = [&](const uint4 (&wreg)[U]) {
-    if (refresh) {  // group boundary (warp-uniform): rebuild the per-column constants, prefetch the next group's
+  // ---- one batch: U steps out of window slots [W0, W0 + U); `step` is the index of its first step ------------------------------
+  auto process = [&](auto w0_tag, int step) {
+    constexpr int W0 = decltype(w0_tag)::value;
+    if (refresh) {  // group boundary (warp-uniform): convert the prefetched raw metadata, prefetch the next group's
+      A s4[VEC];
+      *reinterpret_cast<uint2*>(s4) = raw_s;
+      float z[VEC];
+      A zf[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        cq[j] = make_colq<A, BITS, ORD, FZP>(raw_s[j], raw_z[j] + fbias, raw_zf[j]);
-        sc[j] = ActOps<A>::to_float(raw_s[j]);
+        z[j] = zscalar;
+        zf[j] = zfscalar;
+      }
+      if (zp_per_group) {
+        if constexpr (ZK == CB200_ZP_I32) {
+          z[0] = float(int(raw_z.x)); z[1] = float(int(raw_z.y)); z[2] = float(int(raw_z.z)); z[3] = float(int(raw_z.w));
+        } else if constexpr (ZK == CB200_ZP_U8) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) z[j] = float((raw_z.x >> (8 * j)) & 0xffu);
+        } else if constexpr (ZK == CB200_ZP_ACT) {
+          *reinterpret_cast<uint2*>(zf) = make_uint2(raw_z.x, raw_z.y);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if constexpr (FUSED) {
+          sc[j] = ActOps<A>::to_float(s4[j]);
+          zb[j] = (FZP ? ActOps<A>::to_float(zf[j]) : z[j]) + fbias;
+        } else {
+          cq[j] = make_colq<A, BITS, ORD, FZP>(s4[j], z[j] + fbias, zf[j]);
+        }
       }
       refresh = false;
-      // next group: next row of the metadata, or row 0 of the next column block
-      uint32_t nmeta = meta + N;
-      if (grp + 1 == ngrp) nmeta = uint32_t(cb + 1) * CW + lane_col;
-      if (grp + 1 < ngrp || cb + 1 < geo.col_blocks) fetch_meta(nmeta);
-      meta = nmeta;
+      if (groups_fetched < ngroups_mine) {
+        if (tig == 0 && groups_fetched + 3 < ngroups_mine) {
+          prefetch_l2(sptr + size_t(3) * N);
+          if (zp_per_group) prefetch_l2(zptr + 3 * z_row_bytes);
+        }
+        fetch_meta();
+        ++groups_fetched;
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      // activations of this step: 16 B (8 B for int8) per lane through L1, permuted to the lop3 nibble order
+      // this step's weights leave the window; its slot is re-loaded with the step WIN ahead right away
+      const uint4 wv = win[W0 + u];
+      if (step + u + WIN < nsteps) win[W0 + u] = ldg_stream_v4(wp + (W0 + u) * step_bytes);
+      // activations of this step (prefetched), permuted to the lop3 nibble order; then prefetch the next step's
+      uint32_t xb[MT][PAIRS];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        if (m_ok[mt]) {
+        if constexpr (BITS == 4) {
+          xb[mt][0] = __byte_perm(xnext[mt].x, xnext[mt].z, 0x5410);  // (k0,k4)
+          xb[mt][1] = __byte_perm(xnext[mt].x, xnext[mt].z, 0x7632);  // (k1,k5)
+          xb[mt][2] = __byte_perm(xnext[mt].y, xnext[mt].w, 0x5410);  // (k2,k6)
+          xb[mt][3] = __byte_perm(xnext[mt].y, xnext[mt].w, 0x7632);  // (k3,k7)
+        } else {
+          xb[mt][0] = xnext[mt].x;
+          xb[mt][1] = xnext[mt].y;
+        }
+        if (m_ok[mt] && step + u + 1 < nsteps) {
           if constexpr (BITS == 4) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(xp[mt] + u * (4 * PF)));
-            xb[mt][0] = __byte_perm(v.x, v.z, 0x5410);  // (k0,k4)
-            xb[mt][1] = __byte_perm(v.x, v.z, 0x7632);  // (k1,k5)
-            xb[mt][2] = __byte_perm(v.y, v.w, 0x5410);  // (k2,k6)
-            xb[mt][3] = __byte_perm(v.y, v.w, 0x7632);  // (k3,k7)
+            xnext[mt] = __ldg(reinterpret_cast<const uint4*>(xp[mt]));
           } else {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(xp[mt] + u * (4 * PF)));
-            xb[mt][0] = v.x;
-            xb[mt][1] = v.y;
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(xp[mt]));
+            xnext[mt].x = t.x;
+            xnext[mt].y = t.y;
           }
         }
+        xp[mt] += 4 * PF;
       }
-      const uint32_t words[VEC] = {wreg[u].x, wreg[u].y, wreg[u].z, wreg[u].w};
+      const uint32_t words[VEC] = {wv.x, wv.y, wv.z, wv.w};
       uint32_t d[VEC][PAIRS];
+      const bool fresh = !group_open && u == 0;  // first MMA of a group starts from zero instead of clearing registers
+      if constexpr (FUSED) {
+        // magic-number operands, no arithmetic: fp16 0x6400|q (and 0x6400|(q<<4) for odd nibbles), bf16 0x4300|q
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        if constexpr (SA) {
-          dequant_word_int<A, BITS, ORD, FZP>(words[j], cq[j], d[j]);
-        } else {
-          dequant_word<A, BITS, ORD, FZP>(words[j], cq[j], d[j]);
+        for (int j = 0; j < VEC; ++j) {
+          if constexpr (BITS == 4 && std::is_same<A, __half>::value) {
+            const uint32_t t8 = words[j] >> 8;
+            d[j][0] = lop3_and_or(words[j], 0x000f000fu, 0x64006400u);  // (1024+k0   , 1024+k4)
+            d[j][1] = lop3_and_or(words[j], 0x00f000f0u, 0x64006400u);  // (1024+16k1 , 1024+16k5)
+            d[j][2] = lop3_and_or(t8, 0x000f000fu, 0x64006400u);        // (k2, k6)
+            d[j][3] = lop3_and_or(t8, 0x00f000f0u, 0x64006400u);        // (16k3, 16k7)
+          } else if constexpr (BITS == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[j][i] = lop3_and_or(words[j] >> (4 * i), 0x000f000fu, 0x43004300u);  // (128+k_i, 128+k_i+4)
+          } else {
+            d[j][0] = prmt(words[j], 0x64646464u, 0x4140u);  // (1024+k0, 1024+k1)
+            d[j][1] = prmt(words[j], 0x64646464u, 0x4342u);  // (1024+k2, 1024+k3)
+          }
         }
-      }
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
+          if constexpr (TWO) {
+            // plain nibbles (pairs 0,2) and x16 nibbles (pairs 1,3) accumulate separately
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          // rows g8 of the MMA <- column 2t of this lane, rows g8+8 <- column 2t+1
-#pragma unroll
-          for (int h = 0; h < PAIRS / 2; ++h) {
-            if constexpr (SA) {
-              if (!group_open && u == 0 && h == 0) {
-                mma16816<A>(accg[t][mt], zero4, d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
-                            d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
+            for (int t = 0; t < NT; ++t) {
+              if (fresh) {
+                mma16816<A>(accg[0][t][mt], zero4, d[2 * t][0], d[2 * t + 1][0], d[2 * t][2], d[2 * t + 1][2], xb[mt][0], xb[mt][2]);
+                mma16816<A>(accg[1][t][mt], zero4, d[2 * t][1], d[2 * t + 1][1], d[2 * t][3], d[2 * t + 1][3], xb[mt][1], xb[mt][3]);
               } else {
-                mma16816<A>(accg[t][mt], accg[t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
-                            d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
+                mma16816<A>(accg[0][t][mt], accg[0][t][mt], d[2 * t][0], d[2 * t + 1][0], d[2 * t][2], d[2 * t + 1][2], xb[mt][0], xb[mt][2]);
+                mma16816<A>(accg[1][t][mt], accg[1][t][mt], d[2 * t][1], d[2 * t + 1][1], d[2 * t][3], d[2 * t + 1][3], xb[mt][1], xb[mt][3]);
               }
+            }
+            if (fresh) {
+              mma16816<A>(xs[0][mt], zero4, ONES, ONES, ONES, ONES, xb[mt][0], xb[mt][2]);
+              mma16816<A>(xs[1][mt], zero4, ONES, ONES, ONES, ONES, xb[mt][1], xb[mt][3]);
             } else {
+              mma16816<A>(xs[0][mt], xs[0][mt], ONES, ONES, ONES, ONES, xb[mt][0], xb[mt][2]);
+              mma16816<A>(xs[1][mt], xs[1][mt], ONES, ONES, ONES, ONES, xb[mt][1], xb[mt][3]);
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < PAIRS / 2; ++h) {
+#pragma unroll
+              for (int t = 0; t < NT; ++t) {
+                if (fresh && h == 0) {
+                  mma16816<A>(accg[0][t][mt], zero4, d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1], d[2 * t + 1][2 * h + 1],
+                              xb[mt][2 * h], xb[mt][2 * h + 1]);
+                } else {
+                  mma16816<A>(accg[0][t][mt], accg[0][t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
+                              d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
+                }
+              }
+              if (fresh && h == 0) {
+                mma16816<A>(xs[0][mt], zero4, ONES, ONES, ONES, ONES, xb[mt][2 * h], xb[mt][2 * h + 1]);
+              } else {
+                mma16816<A>(xs[0][mt], xs[0][mt], ONES, ONES, ONES, ONES, xb[mt][2 * h], xb[mt][2 * h + 1]);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) dequant_word<A, BITS, ORD, FZP>(words[j], cq[j], d[j]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            // rows g8 of the MMA <- column 2t of this lane, rows g8+8 <- column 2t+1
+#pragma unroll
+            for (int h = 0; h < PAIRS / 2; ++h) {
               mma16816<A>(acc[t][mt], acc[t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
                           d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
             }
@@ -335,62 +397,73 @@ __global__ void __launch_bounds__(128, MT == 1 ? 6 : 4)
     }
     group_open = true;
     if (--batches_left == 0) {  // group finished
-      if constexpr (SA) close_group();
+      if constexpr (FUSED) close_group();
       group_open = false;
       batches_left = bpg;
       refresh = true;
-      ++grp;
     }
   };
 
-  // advance (cb, b, xp) to the next unit; returns true when that unit starts a new column block
-  auto advance = [&]() {
-    ++b;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) xp[mt] += U * 4 * PF;
-    if (b != B) return false;
-    b = 0;
-    ++cb;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) xp[mt] -= p.K;
-    return true;
-  };
-  auto end_column = [&](int cbi) {  // always on a group boundary
-    flush(cbi);
+  // ---- main loop: two batches (the whole window) per iteration ------------------------------------------------------------------
+  for (int i = 0; i < nunits; i += 2) {
+    process(std::integral_constant<int, 0>{}, i * U);
+    if (i + 1 < nunits) process(std::integral_constant<int, U>{}, (i + 1) * U);
+    wp += WIN * step_bytes;
+  }
+  if constexpr (FUSED) {
+    if (group_open) close_group();  // slab ended inside a group (per-channel scales split across warps)
+  }
+
+  // ---- publish -----------------------------------------------------------------------------------------------------------------
+  if (S == 1) {  // this warp saw the whole K range: store directly
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[t][mt][k] = 0.f;
-    grp = 0;
-  };
-
-  // ---- main loop: unit i is consumed from ring slot i % SLOTS while unit i + LOOK is being fetched ---------------------
-  int slot = 0, islot = LOOK % SLOTS;
-  for (int i = 0; i < n_units; ++i) {
-    if (i + LOOK < n_units) issue_unit(islot);
-    asm volatile("cp.async.commit_group;" ::: "memory");  // always commit (possibly empty): keeps the group count static
-    islot = islot + 1 == SLOTS ? 0 : islot + 1;
-    asm volatile("cp.async.wait_group %0;" ::"n"(LOOK) : "memory");  // everything but the newest LOOK groups has landed
-    uint4 wreg[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(wreg[u].x), "=r"(wreg[u].y), "=r"(wreg[u].z), "=r"(wreg[u].w)
-                   : "r"(ring + (slot * U + u) * 512));
-    }
-    slot = slot + 1 == SLOTS ? 0 : slot + 1;
-    process(wreg);
-    const int done_cb = cb;
-    if (advance()) end_column(done_cb);
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m = mt * 8 + 2 * tig;
+        const int n = col + 2 * t;
+        if (m < M) {
+          store_out<A>(p.out, p.out_dtype, size_t(m) * N + n, acc[t][mt][0]);
+          store_out<A>(p.out, p.out_dtype, size_t(m) * N + n + 1, acc[t][mt][2]);
+        }
+        if (m + 1 < M) {
+          store_out<A>(p.out, p.out_dtype, size_t(m + 1) * N + n, acc[t][mt][1]);
+          store_out<A>(p.out, p.out_dtype, size_t(m + 1) * N + n + 1, acc[t][mt][3]);
+        }
+      }
+    return;
   }
-  if (b != 0) {  // range ended inside a column block: close the open group (SA) and publish the partial
-    if constexpr (SA) {
-      if (group_open) close_group();
+  float* mine = ws_partial + (size_t(cb) * S + si) * (M * CW);
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int m = mt * 8 + 2 * tig;
+      const int lc = VEC * g8 + 2 * t;
+      if (m < M) {
+        __stcg(mine + m * CW + lc, acc[t][mt][0]);
+        __stcg(mine + m * CW + lc + 1, acc[t][mt][2]);
+      }
+      if (m + 1 < M) {
+        __stcg(mine + (m + 1) * CW + lc, acc[t][mt][1]);
+        __stcg(mine + (m + 1) * CW + lc + 1, acc[t][mt][3]);
+      }
     }
-    flush(cb);
+  __threadfence();
+  __syncwarp();
+  unsigned prev = 0;
+  if (lane == 0) prev = atomicAdd(ws_counter + cb, 1u);
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev != unsigned(S - 1)) return;
+  __threadfence();  // last arriver: every other slab's partial is visible now
+  const float* base = ws_partial + size_t(cb) * S * (M * CW);
+  for (int e = lane; e < M * CW; e += 32) {
+    float v = 0.f;
+    for (int s = 0; s < S; ++s) v += __ldcg(base + size_t(s) * (M * CW) + e);
+    const int m = e / CW, lc = e - m * CW;
+    store_out<A>(p.out, p.out_dtype, size_t(m) * N + cb * CW + lc, v);
   }
+  if (lane == 0) ws_counter[cb] = 0u;  // leave the counter clean for the next launch
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -398,84 +471,111 @@ __global__ void __launch_bounds__(128, MT == 1 ? 6 : 4)
 // ------------------------------------------------------------------------------------------------------------
 static int pick(int forced, int heuristic) { return forced > 0 ? forced : heuristic; }
 
+int g_decode_pdl = 0;
+
 struct DecodePlan {
-  int u;            // steps per batch (4, or 2 for int4 with g = 64)
-  int units_per_col, col_blocks, total_units;
-  int total_warps, q, r, slots_max;
-  bool scale_after;
+  int u;               // steps per batch (4, or 2 for int4 with g = 64)
+  int bpg;             // batches per scale group
+  int splits, units_per_warp, col_blocks, total_warps;
+  int ctas_per_sm;
+  bool fused;
 };
 
-// Every knob is overridable through cb200_set_decode_tuning(warps_n -> 1: force in-loop scaling (bit-exact W),
-// 2: force scale-after; warps_k -> CTAs per SM assumed resident; split_k -> units per warp; vec_words unused).
+// Every knob is overridable through cb200_set_decode_tuning(warps_n -> 1 (default): per-weight dequant before the MMA (W
+// bits identical to the reference's w_ref), 2: fused magic-number operands; warps_k -> CTAs per SM assumed resident;
+// split_k -> forced split count S (rounded down to a legal divisor); vec_words unused).
 static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
   DecodePlan pl;
   const int step_k = 4 * (32 / bits);
   pl.u = (g % (4 * step_k) == 0) ? 4 : 2;
-  pl.units_per_col = K / (pl.u * step_k);
+  const int B = K / (pl.u * step_k);  // batches per column block
+  pl.bpg = g / (pl.u * step_k);
   pl.col_blocks = N / 32;
-  pl.total_units = pl.units_per_col * pl.col_blocks;
-  const int ctas_per_sm = pick(g_decode_tuning.warps_k, mrows > 8 ? 4 : 6);
-  const int capacity = 148 * ctas_per_sm * 4;  // co-resident warps
-  int per_warp = (pl.total_units + capacity - 1) / capacity;
-  if (per_warp < 2 && pl.total_units >= 2 * 148 * 4) per_warp = 2;  // tiny problems: still two batches per warp
-  per_warp = pick(g_decode_tuning.split_k, per_warp);
-  if (per_warp > pl.total_units) per_warp = pl.total_units;
-  pl.total_warps = (pl.total_units + per_warp - 1) / per_warp;
-  pl.q = pl.total_units / pl.total_warps;
-  pl.r = pl.total_units % pl.total_warps;
-  // a column block of B units is covered by at most ceil(B / q) + 1 warps
-  pl.slots_max = (pl.units_per_col + pl.q - 1) / pl.q + 1;
-  pl.scale_after = g_decode_tuning.warps_n == 1 ? false : true;
+  pl.fused = g_decode_tuning.warps_n == 2;
+  // __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
+  pl.ctas_per_sm = pick(g_decode_tuning.warps_k, mrows > 8 ? 3 : (pl.fused ? 4 : 5));
+  const int capacity = 148 * pl.ctas_per_sm * 4;  // co-resident warps
+  // S must divide B, and a slab must not cut a group unless the group spans whole slabs (per-channel / huge groups):
+  // legal S: (B / S) % bpg == 0  or  bpg % (B / S) == 0.  Pick the largest legal S that keeps one wave and >= 2 batches.
+  int best = 1;
+  for (int sdiv = 1; sdiv <= B; ++sdiv) {
+    if (B % sdiv) continue;
+    const int per = B / sdiv;
+    if (!(per % pl.bpg == 0 || pl.bpg % per == 0)) continue;
+    if (g_decode_tuning.split_k > 0) {
+      if (sdiv <= g_decode_tuning.split_k) best = sdiv;
+      continue;
+    }
+    const int64_t warps = int64_t(pl.col_blocks) * sdiv;
+    if (warps > 3 * int64_t(capacity)) break;           // at most ~3 waves of resident warps
+    if (warps > capacity && per < 4) break;             // beyond one wave only while a warp still streams >= 4 batches
+    if (per < 2 && sdiv > 1) break;
+    best = sdiv;
+  }
+  pl.splits = best;
+  pl.units_per_warp = B / best;
+  pl.total_warps = pl.col_blocks * best;
   return pl;
 }
 
 size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits) {
   const int mrows = int(M < 16 ? M : 16);
-  // the group size changes the plan only through U; take the larger footprint of the two
-  size_t need = 0;
-  for (int g : {64, 128}) {
-    if (K % g) continue;
-    const DecodePlan pl = decode_plan(mrows, int(K), int(N), bits, g);
-    const size_t b = size_t(pl.col_blocks) * pl.slots_max * mrows * 32 * sizeof(float);
-    need = b > need ? b : need;
-  }
-  return size_t(CB200_WORKSPACE_COUNTER_BYTES) + need;
+  // the group size changes the plan through U and the legal splits; bound by the finest legal split (one batch per warp)
+  const int step_k = 4 * (32 / bits);
+  const size_t max_splits = size_t(K) / (2 * step_k);
+  const size_t capacity = size_t(148) * 6 * 4;
+  size_t splits = 3 * capacity / size_t(N / 32) + 1;
+  if (splits > max_splits) splits = max_splits;
+  if (g_decode_tuning.split_k > 0) splits = max_splits;
+  return size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(N / 32) * splits * mrows * 32 * sizeof(float);
 }
 
 template <class A, int BITS, int MT, int U, int ZK>
-static int launch_sa(bool sa, const Problem& p, const DecodeGeom& geo, int blocks, float* wsp, unsigned* wsc,
-                     cudaStream_t stream) {
-  constexpr size_t smem = size_t(4) * kDecodeRingSteps * 512;  // 4 warps x ring
-  if (sa) {
-    decode_kernel<A, BITS, MT, U, ZK, true><<<blocks, 128, smem, stream>>>(p, geo, wsp, wsc);
+static int launch_fused(bool fused, const Problem& p, const DecodeGeom& geo, int blocks, size_t smem, float* wsp,
+                        unsigned* wsc, cudaStream_t stream) {
+  void (*kern)(const Problem, const DecodeGeom, float*, unsigned int*);
+  // bf16 x int8: 128 + q does not fit a bf16 significand, so there is no magic-number operand -> per-weight dequant
+  if (fused && !(std::is_same<A, __nv_bfloat16>::value && BITS == 8)) {
+    kern = decode_kernel<A, BITS, MT, U, ZK, true>;
   } else {
-    decode_kernel<A, BITS, MT, U, ZK, false><<<blocks, 128, smem, stream>>>(p, geo, wsp, wsc);
+    kern = decode_kernel<A, BITS, MT, U, ZK, false>;
   }
-  CB200_CUDA_CHECK(cudaGetLastError());
+  if (smem > 48 * 1024) CB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = geo.pdl ? 1 : 0;
+  CB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p, geo, wsp, wsc));
   return 0;
 }
 
 template <class A, int BITS, int MT, int U>
-static int launch_zk(bool sa, const Problem& p, const DecodeGeom& geo, int blocks, float* wsp, unsigned* wsc,
+static int launch_zk(bool fused, const Problem& p, const DecodeGeom& geo, int blocks, size_t smem, float* wsp, unsigned* wsc,
                      cudaStream_t stream) {
   switch (p.zp_kind) {
-    case CB200_ZP_NONE: return launch_sa<A, BITS, MT, U, CB200_ZP_NONE>(sa, p, geo, blocks, wsp, wsc, stream);
-    case CB200_ZP_I32: return launch_sa<A, BITS, MT, U, CB200_ZP_I32>(sa, p, geo, blocks, wsp, wsc, stream);
-    case CB200_ZP_U8: return launch_sa<A, BITS, MT, U, CB200_ZP_U8>(sa, p, geo, blocks, wsp, wsc, stream);
-    default: return launch_sa<A, BITS, MT, U, CB200_ZP_ACT>(false, p, geo, blocks, wsp, wsc, stream);
+    case CB200_ZP_NONE: return launch_fused<A, BITS, MT, U, CB200_ZP_NONE>(fused, p, geo, blocks, smem, wsp, wsc, stream);
+    case CB200_ZP_I32: return launch_fused<A, BITS, MT, U, CB200_ZP_I32>(fused, p, geo, blocks, smem, wsp, wsc, stream);
+    case CB200_ZP_U8: return launch_fused<A, BITS, MT, U, CB200_ZP_U8>(fused, p, geo, blocks, smem, wsp, wsc, stream);
+    default: return launch_fused<A, BITS, MT, U, CB200_ZP_ACT>(fused, p, geo, blocks, smem, wsp, wsc, stream);
   }
 }
 
 template <class A, int BITS>
-static int launch_typed(int u, bool sa, const Problem& p, const DecodeGeom& geo, int blocks, float* wsp, unsigned* wsc,
-                        cudaStream_t stream) {
+static int launch_typed(int u, bool fused, const Problem& p, const DecodeGeom& geo, int blocks, size_t smem, float* wsp,
+                        unsigned* wsc, cudaStream_t stream) {
   const bool mt2 = geo.m_rows > 8;
   if (u == 4) {
-    return mt2 ? launch_zk<A, BITS, 2, 4>(sa, p, geo, blocks, wsp, wsc, stream)
-               : launch_zk<A, BITS, 1, 4>(sa, p, geo, blocks, wsp, wsc, stream);
+    return mt2 ? launch_zk<A, BITS, 2, 4>(fused, p, geo, blocks, smem, wsp, wsc, stream)
+               : launch_zk<A, BITS, 1, 4>(fused, p, geo, blocks, smem, wsp, wsc, stream);
   }
-  return mt2 ? launch_zk<A, BITS, 2, 2>(sa, p, geo, blocks, wsp, wsc, stream)
-             : launch_zk<A, BITS, 1, 2>(sa, p, geo, blocks, wsp, wsc, stream);
+  return mt2 ? launch_zk<A, BITS, 2, 2>(fused, p, geo, blocks, smem, wsp, wsc, stream)
+             : launch_zk<A, BITS, 1, 2>(fused, p, geo, blocks, smem, wsp, wsc, stream);
 }
 
 int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream,
@@ -490,8 +590,8 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
 
     const DecodePlan pl = decode_plan(mrows, p.K, p.N, bits, p.g);
     const size_t need =
-        size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.col_blocks) * pl.slots_max * mrows * 32 * sizeof(float);
-    if (ws == nullptr || ws_bytes < need) {
+        size_t(CB200_WORKSPACE_COUNTER_BYTES) + (pl.splits > 1 ? size_t(pl.total_warps) * mrows * 32 * sizeof(float) : 0);
+    if (pl.splits > 1 && (ws == nullptr || ws_bytes < need)) {
       set_error("decode kernel needs %zu workspace bytes, got %zu", need, ws_bytes);
       return CB200_ERR_WORKSPACE;
     }
@@ -499,24 +599,27 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
       set_error("N=%d too large for the split-K counter area", p.N);
       return CB200_ERR_SHAPE;
     }
+    if (size_t(p.K / p.g) * p.N >= (size_t(1) << 31)) {
+      set_error("scale matrix too large");
+      return CB200_ERR_SHAPE;
+    }
     DecodeGeom geo;
     geo.m_rows = mrows;
-    geo.units_per_col = pl.units_per_col;
-    geo.q = pl.q;
-    geo.r = pl.r;
+    geo.splits = pl.splits;
+    geo.units_per_warp = pl.units_per_warp;
     geo.total_warps = pl.total_warps;
-    geo.col_blocks = pl.col_blocks;
-    geo.slots_max = pl.slots_max;
+    geo.bpg = pl.bpg;
+    geo.pdl = g_decode_pdl;
     const int blocks = (pl.total_warps + 3) / 4;
-    float* wsp = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES);
+    float* wsp = ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES) : nullptr;
     unsigned* wsc = reinterpret_cast<unsigned*>(ws);
     int rc;
     if (act_dtype == CB200_F16) {
-      rc = bits == 4 ? launch_typed<__half, 4>(pl.u, pl.scale_after, p, geo, blocks, wsp, wsc, stream)
-                     : launch_typed<__half, 8>(pl.u, pl.scale_after, p, geo, blocks, wsp, wsc, stream);
+      rc = bits == 4 ? launch_typed<__half, 4>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream)
+                     : launch_typed<__half, 8>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream);
     } else {
-      rc = bits == 4 ? launch_typed<__nv_bfloat16, 4>(pl.u, pl.scale_after, p, geo, blocks, wsp, wsc, stream)
-                     : launch_typed<__nv_bfloat16, 8>(pl.u, pl.scale_after, p, geo, blocks, wsp, wsc, stream);
+      rc = bits == 4 ? launch_typed<__nv_bfloat16, 4>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream)
+                     : launch_typed<__nv_bfloat16, 8>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream);
     }
     if (rc != 0) return rc;
     if (launches) ++*launches;

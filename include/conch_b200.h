@@ -108,6 +108,12 @@ CB200_API void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, in
 /* Debug/tuning knobs for the tcgen05 family: m_tile (MMA N: 16..256, 0 = heuristic), split_k (0 = heuristic). */
 CB200_API void cb200_set_tc_tuning(int m_tile, int split_k);
 
+/* Programmatic dependent launch for the decode kernels (default off).  When enabled, a decode kernel may start while the
+ * previous kernel in the stream is still draining and prefetches its WEIGHTS, scales and zero-points before waiting for
+ * that kernel; x, out and the workspace are only touched afterwards.  The caller thereby asserts that w_q_packed / w_s /
+ * w_zp are not written by the kernel enqueued immediately before the call (true for inference: weights are static). */
+CB200_API void cb200_set_pdl(int enable);
+
 #ifdef __cplusplus
 }
 #endif
