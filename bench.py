@@ -220,6 +220,9 @@ def run_gpu_arm(args) -> None:
     if world > 1:
         dist.barrier()
     lib = _lib.load()
+    # Programmatic dependent launch: each GEMV prefetches its (static) weights while the previous one drains.
+    # Legal here because no kernel in the step writes weights (include/conch_b200.h, cb200_set_pdl).
+    lib.cb200_set_pdl(0 if args.no_pdl else 1)
 
     # ---- synthetic model: 32 layers x 4 projections, drawn directly in the packed domain ------------------------
     st = quant_utils.scalar_types.uint4
@@ -366,7 +369,8 @@ def run_gpu_arm(args) -> None:
             "config": {
                 "workload": WORKLOAD,
                 "M": M,
-                "launch": "cuda-graph replay of the 128 GEMV launches" if graph is not None else "eager python launches",
+                "launch": ("cuda-graph replay of the 128 GEMV launches" if graph is not None else "eager python launches")
+                + ("" if args.no_pdl else ", programmatic dependent launch"),
                 "l2": "inputs larger than L2: 3.49 GB of packed weights per step vs 126 MB L2",
                 "sharding": "none" if world == 1 else f"N-sharded x{world}, NCCL all_gather_into_tensor after every GEMM",
             },
@@ -379,7 +383,7 @@ def run_gpu_arm(args) -> None:
                 "frac": per_gpu / peak,
                 "traffic": traffic,
                 "peak_source": peak_src,
-                "kernel": "cb200::decode_kernel<__half,4,1,2,false>",
+                "kernel": "cb200::decode_kernel<__half,4,1,4,CB200_ZP_I32,false>",
                 "algorithmic_bytes_per_launch": algorithmic_bytes() / (LAYERS * len(PROJECTIONS)),
                 "avg_launch_us": ms_per_step * 1e3 / (LAYERS * len(PROJECTIONS)),
             },
@@ -400,8 +404,12 @@ def run_gpu_arm(args) -> None:
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # NCCL collectives captured in the CUDA graph keep communicator resources alive; tearing the process group
+        # down under them can hang.  Everything is measured and printed: drain, then leave without the teardown.
+        sys.stdout.flush()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main() -> None:
@@ -412,6 +420,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-graph", action="store_true", help="time eager Python launches instead of a CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between the GEMVs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

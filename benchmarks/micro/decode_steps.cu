@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <vector>
 
+#include "../../conch_b200/csrc/dequant.cuh"
+
 __device__ __forceinline__ uint4 ldg_na(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -43,7 +45,19 @@ __device__ __forceinline__ void consume(const uint4 (&w)[4], float (&acc)[6][4],
         d[j][2] = lop(t8, 0x000f000fu, 0x64006400u);
         d[j][3] = lop(t8, 0x00f000f0u, 0x64006400u);
       }
-      if constexpr (COMPUTE == 1) {
+      if constexpr (COMPUTE == 3) {
+        cb200::ColQ cq;
+        cq.s = 0x1C001C00u; cq.c0 = 0x64086408u; cq.c1 = 0xD480D480u; cq.zf = 0;
+        uint32_t e[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cb200::dequant_word<__half, 4, cb200::Order::Lop, false>(words[j], cq, e[j]);
+        const uint32_t xb0 = 0x3C003C00u + u, xb1 = 0x3C003C00u, xb2 = 0x3C003C01u, xb3 = 0x3C003C02u;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mma(acc[t], e[2 * t][0], e[2 * t + 1][0], e[2 * t][1], e[2 * t + 1][1], xb0, xb1);
+          mma(acc[t], e[2 * t][2], e[2 * t + 1][2], e[2 * t][3], e[2 * t + 1][3], xb2, xb3);
+        }
+      } else if constexpr (COMPUTE == 1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) x ^= d[j][0] ^ d[j][1] ^ d[j][2] ^ d[j][3];
       } else {
@@ -92,6 +106,27 @@ __global__ void __launch_bounds__(128) k(const uint32_t* __restrict__ wq, int N,
       }
       consume<COMPUTE>(b, acc, x);
     }
+  } else if constexpr (LOADER == 2) {
+    const int nsteps = nunits * 4;
+    uint4 win[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { win[j] = make_uint4(0, 0, 0, 0); if (j < nsteps) win[j] = ldg_na(p + j * step_bytes); }
+    p += 8 * step_bytes;
+    for (int i = 0; i < nunits; i += 2) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (i + h < nunits) {
+          uint4 a[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a[u] = win[4 * h + u];
+            if ((i + h) * 4 + u + 8 < nsteps) win[4 * h + u] = ldg_na(p + (4 * h + u) * step_bytes);
+          }
+          consume<COMPUTE>(a, acc, x);
+        }
+      }
+      p += 8 * step_bytes;
+    }
   } else {
     constexpr int SLOTS = LOOK + 1;
     const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring_raw)) + (threadIdx.x >> 5) * (SLOTS * 2048) + lane * 16;
@@ -122,7 +157,7 @@ __global__ void __launch_bounds__(128) k(const uint32_t* __restrict__ wq, int N,
   float s = float(x);
 #pragma unroll
   for (int i = 0; i < 6; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
-  if (s == 12345.678f) out[w] = s;
+  if (s == 12345.678f || x == 0x9e3779b9u) out[w] = s;
 }
 
 __global__ void fill_random(unsigned* p, size_t n, unsigned seed) {
@@ -162,6 +197,10 @@ int main(int argc, char** argv) {
     run(k<0, 0, 1>, "regs dbuf, xor", S, 1, 0);
     run(k<0, 1, 1>, "regs dbuf, lop3", S, 1, 0);
     run(k<0, 2, 1>, "regs dbuf, lop3+6 HMMA", S, 1, 0);
+    run(k<0, 3, 1>, "regs dbuf, dequant_word+4 HMMA", S, 1, 0);
+    run(k<2, 0, 1>, "regs window8, xor", S, 1, 0);
+    run(k<2, 2, 1>, "regs window8, lop3+6 HMMA", S, 1, 0);
+    run(k<2, 3, 1>, "regs window8, dequant_word+4 HMMA", S, 1, 0);
     run(k<1, 0, 1>, "cp.async LOOK=1, xor", S, 1, 2 * 2048);
     run(k<1, 0, 2>, "cp.async LOOK=2, xor", S, 2, 3 * 2048);
     run(k<1, 0, 4>, "cp.async LOOK=4, xor", S, 4, 5 * 2048);

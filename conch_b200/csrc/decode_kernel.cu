@@ -14,15 +14,15 @@
 //     All cursors are linear pointer increments;
 //   * FUSED=false: nibbles are unpacked and W = (q - bias - zp) * s is formed per weight with dequant_word() -- the
 //     same bits as the dequant kernel and the reference's w_ref -- before the MMA;
-//   * FUSED=true (opt-in, cb200_set_decode_tuning(2,..): fewer instructions per weight but, as compiled today, 128
-//     registers per thread and lower occupancy -- measured slower than FUSED=false, kept for round 2): the
-//     magic-number operand itself, 0x6400|q = 1024 + q (fp16) or 0x4300|q = 128 + q (bf16), goes into the MMA, so a word
-//     costs 1 shift + 4 lop3 and NO floating-point op.  One extra MMA per step with an all-ones A operand yields
-//     X = sum_k x_k in the same fragment layout, and at each group boundary
-//         acc += s[n] * ( D[n,m] - MAGIC * X[m] - (bias + zp[n]) * X[m] )
-//     (fp16 int4 keeps the x16-scaled odd nibbles in a second accumulator: D = D_even + D_odd / 16, offsets 1024 / 64).
-//     sum_k x_k q_k is exact in the tensor core; the result differs from the reference only by not rounding each W to
-//     fp16/bf16 and by fp32 cancellation of the MAGIC * X term (~1e-5 relative), far inside the 1e-2 tolerance;
+//   * FUSED=true: the magic-number operand itself, 0x6400|q = 1024 + q (fp16) or 0x4300|q = 128 + q (bf16), goes into
+//     the MMA, so a word costs 1 shift + 4 lop3 and NO floating-point op.  The offset is removed inside the tensor core
+//     too: a second MMA per operand pair multiplies the same activations with the per-column constant -(MAGIC + bias + zp)
+//     into the SAME accumulator, which therefore holds sum_k x_k (q_k - bias - zp) exactly (products of small integers
+//     and fp16/bf16 values are exact in fp32).  fp16 int4's odd nibbles arrive as 1024 + 16 q; their activations are
+//     pre-multiplied by 1/16 (exact except in the subnormal range, where the error cancels between the two MMAs).  The
+//     group scale is applied once per group to the fp32 sum: acc += s[n] * group_sum.  The result differs from the
+//     reference only by not rounding each W to fp16/bf16 -- far inside the 1e-2 tolerance; one-hot activations still
+//     reproduce the reference's W bit for bit;
 //   * the dot product runs on the tensor pipe as mma.sync.m16n8k16 with the WEIGHTS as the 16-row operand (swap-AB) and
 //     x^T as the 8-column operand; the four lanes of a quad hold four different packed rows, so the K-reduction
 //     across lanes happens inside the MMA, fp32 accumulate; x is permuted in registers to the nibble order the cheap
@@ -80,8 +80,6 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   constexpr int WIN = 2 * U;        // weight loads in flight per lane (steps)
   constexpr Order ORD = Order::Lop;
   constexpr bool FZP = ZK == CB200_ZP_ACT;
-
-  if (geo.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the next kernel's CTAs queue up
 
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -184,64 +182,34 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   int batches_left = bpg - (b0 % bpg);  // batches until the current group ends
   bool refresh = true;
   const float fbias = float(p.bias);
-  // FUSED layout: fp16/int4 has two operand kinds per word (plain and x16 nibbles) -> two accumulators
-  constexpr bool TWO = FUSED && std::is_same<A, __half>::value && BITS == 4;
-  constexpr float MAGIC = std::is_same<A, __half>::value ? 1024.f : 128.f;
-  constexpr uint32_t ONES = std::is_same<A, __half>::value ? 0x3C003C00u : 0x3F803F80u;  // (1.0, 1.0)
-  constexpr int NACC = TWO ? 2 : 1;
+  constexpr bool HALF = std::is_same<A, __half>::value;
+  constexpr bool PRESCALE = FUSED && HALF && BITS == 4;  // odd nibbles are 1024 + 16 q: their activations get x 1/16
+  constexpr float MAGIC = HALF ? 1024.f : 128.f;
 
-  ColQ cq[VEC];     // !FUSED: per-column dequant constants
-  float sc[VEC];    // FUSED: group scales as fp32
-  float zb[VEC];    // FUSED: bias + zero-point per column
+  ColQ cq[VEC];          // !FUSED: per-column dequant constants
+  float sc[VEC];         // FUSED: group scales as fp32
+  uint32_t offe[VEC];    // FUSED: pair (-(MAGIC + zb), same) per column           (plain operands)
+  uint32_t offo[VEC];    // FUSED: pair (-(MAGIC + 16 zb), same) per column        (x16 operands, fp16 int4 only)
 
   const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
-  float acc[NT][MT][4];          // running (scaled) sum of this warp's slab
-  float accg[NACC][NT][MT][4];   // FUSED: raw sums of the current group (even / odd operand kinds)
-  float xs[NACC][MT][4];         // FUSED: sum_k x_k of the current group from the all-ones MMA (rows are identical)
+  float acc[NT][MT][4];   // running (scaled) sum of this warp's slab
+  float accg[NT][MT][4];  // FUSED: exact sum_k x_k (q_k - zb) of the current group
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[t][mt][i] = 0.f;
-#pragma unroll
-        for (int a = 0; a < NACC; ++a) accg[a][t][mt][i] = 0.f;
-      }
-#pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xs[a][mt][i] = 0.f;
-  }
-  bool group_open = false;  // FUSED: accg / xs hold a partial group
+      for (int i = 0; i < 4; ++i) acc[t][mt][i] = accg[t][mt][i] = 0.f;
+  bool group_open = false;  // FUSED: accg holds a partial group
 
-  auto close_group = [&]() {  // FUSED: acc += s[n] * (D - offset * X - zb[n] * X)
+  auto close_group = [&]() {  // FUSED: acc += s[n] * group_sum
     // C fragment: c0,c1 <- weight column 2t (m = 2tig, 2tig+1); c2,c3 <- weight column 2t+1 of this lane
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float off[2], xsum[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if constexpr (TWO) {
-          off[j] = fmaf(1024.f, xs[0][mt][j], 64.f * xs[1][mt][j]);
-          xsum[j] = xs[0][mt][j] + xs[1][mt][j];
-        } else {
-          off[j] = MAGIC * xs[0][mt][j];
-          xsum[j] = xs[0][mt][j];
-        }
-      }
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int t = 0; t < NT; ++t)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = 2 * t + (i >> 1), j = i & 1;
-          float d = accg[0][t][mt][i];
-          if constexpr (TWO) d = fmaf(accg[1][t][mt][i], 0.0625f, d);
-          d -= off[j];
-          d = fmaf(-zb[c], xsum[j], d);
-          acc[t][mt][i] = fmaf(sc[c], d, acc[t][mt][i]);
-        }
-    }
+        for (int i = 0; i < 4; ++i) acc[t][mt][i] = fmaf(sc[2 * t + (i >> 1)], accg[t][mt][i], acc[t][mt][i]);
   };
 
   // ---- one batch: U steps out of window slots [W0, W0 + U); `step` is the index of its first step ------------------------------
@@ -271,7 +239,9 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
       for (int j = 0; j < VEC; ++j) {
         if constexpr (FUSED) {
           sc[j] = ActOps<A>::to_float(s4[j]);
-          zb[j] = (FZP ? ActOps<A>::to_float(zf[j]) : z[j]) + fbias;
+          const float zbj = (FZP ? ActOps<A>::to_float(zf[j]) : z[j]) + fbias;
+          offe[j] = ActOps<A>::pair(-(MAGIC + zbj), -(MAGIC + zbj));
+          offo[j] = PRESCALE ? ActOps<A>::pair(-(MAGIC + 16.f * zbj), -(MAGIC + 16.f * zbj)) : offe[j];
         } else {
           cq[j] = make_colq<A, BITS, ORD, FZP>(s4[j], z[j] + fbias, zf[j]);
         }
@@ -322,7 +292,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         // magic-number operands, no arithmetic: fp16 0x6400|q (and 0x6400|(q<<4) for odd nibbles), bf16 0x4300|q
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          if constexpr (BITS == 4 && std::is_same<A, __half>::value) {
+          if constexpr (BITS == 4 && HALF) {
             const uint32_t t8 = words[j] >> 8;
             d[j][0] = lop3_and_or(words[j], 0x000f000fu, 0x64006400u);  // (1024+k0   , 1024+k4)
             d[j][1] = lop3_and_or(words[j], 0x00f000f0u, 0x64006400u);  // (1024+16k1 , 1024+16k5)
@@ -338,43 +308,25 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          if constexpr (TWO) {
-            // plain nibbles (pairs 0,2) and x16 nibbles (pairs 1,3) accumulate separately
+          if constexpr (PRESCALE) {  // activations that meet the x16 operands: x * 1/16
+            xb[mt][1] = ActOps<A>::mul(xb[mt][1], 0x2C002C00u);
+            xb[mt][3] = ActOps<A>::mul(xb[mt][3], 0x2C002C00u);
+          }
+#pragma unroll
+          for (int h = 0; h < PAIRS / 2; ++h) {
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-              if (fresh) {
-                mma16816<A>(accg[0][t][mt], zero4, d[2 * t][0], d[2 * t + 1][0], d[2 * t][2], d[2 * t + 1][2], xb[mt][0], xb[mt][2]);
-                mma16816<A>(accg[1][t][mt], zero4, d[2 * t][1], d[2 * t + 1][1], d[2 * t][3], d[2 * t + 1][3], xb[mt][1], xb[mt][3]);
-              } else {
-                mma16816<A>(accg[0][t][mt], accg[0][t][mt], d[2 * t][0], d[2 * t + 1][0], d[2 * t][2], d[2 * t + 1][2], xb[mt][0], xb[mt][2]);
-                mma16816<A>(accg[1][t][mt], accg[1][t][mt], d[2 * t][1], d[2 * t + 1][1], d[2 * t][3], d[2 * t + 1][3], xb[mt][1], xb[mt][3]);
-              }
-            }
-            if (fresh) {
-              mma16816<A>(xs[0][mt], zero4, ONES, ONES, ONES, ONES, xb[mt][0], xb[mt][2]);
-              mma16816<A>(xs[1][mt], zero4, ONES, ONES, ONES, ONES, xb[mt][1], xb[mt][3]);
-            } else {
-              mma16816<A>(xs[0][mt], xs[0][mt], ONES, ONES, ONES, ONES, xb[mt][0], xb[mt][2]);
-              mma16816<A>(xs[1][mt], xs[1][mt], ONES, ONES, ONES, ONES, xb[mt][1], xb[mt][3]);
-            }
-          } else {
-#pragma unroll
-            for (int h = 0; h < PAIRS / 2; ++h) {
-#pragma unroll
-              for (int t = 0; t < NT; ++t) {
-                if (fresh && h == 0) {
-                  mma16816<A>(accg[0][t][mt], zero4, d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1], d[2 * t + 1][2 * h + 1],
-                              xb[mt][2 * h], xb[mt][2 * h + 1]);
-                } else {
-                  mma16816<A>(accg[0][t][mt], accg[0][t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
-                              d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
-                }
-              }
+              // data: rows g8 <- column 2t, rows g8+8 <- column 2t+1; operand pair 2h is plain, 2h+1 is the x16 kind
               if (fresh && h == 0) {
-                mma16816<A>(xs[0][mt], zero4, ONES, ONES, ONES, ONES, xb[mt][2 * h], xb[mt][2 * h + 1]);
+                mma16816<A>(accg[t][mt], zero4, d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1], d[2 * t + 1][2 * h + 1],
+                            xb[mt][2 * h], xb[mt][2 * h + 1]);
               } else {
-                mma16816<A>(xs[0][mt], xs[0][mt], ONES, ONES, ONES, ONES, xb[mt][2 * h], xb[mt][2 * h + 1]);
+                mma16816<A>(accg[t][mt], accg[t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
+                            d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
               }
+              // offset: the same activations times -(MAGIC + zb) (resp. -(MAGIC + 16 zb)) into the same accumulator
+              mma16816<A>(accg[t][mt], accg[t][mt], offe[2 * t], offe[2 * t + 1], offo[2 * t], offo[2 * t + 1],
+                          xb[mt][2 * h], xb[mt][2 * h + 1]);
             }
           }
         }
@@ -413,6 +365,8 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   if constexpr (FUSED) {
     if (group_open) close_group();  // slab ended inside a group (per-channel scales split across warps)
   }
+  // this warp has issued all of its loads: let the next kernel's CTAs start filling the slots our tail frees
+  if (geo.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- publish -----------------------------------------------------------------------------------------------------------------
   if (S == 1) {  // this warp saw the whole K range: store directly
@@ -507,8 +461,7 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
       continue;
     }
     const int64_t warps = int64_t(pl.col_blocks) * sdiv;
-    if (warps > 3 * int64_t(capacity)) break;           // at most ~3 waves of resident warps
-    if (warps > capacity && per < 4) break;             // beyond one wave only while a warp still streams >= 4 batches
+    if (warps > capacity && best > 0 && sdiv > 1) break;  // one co-resident wave (measured: more waves do not help)
     if (per < 2 && sdiv > 1) break;
     best = sdiv;
   }
@@ -524,7 +477,7 @@ size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits) {
   const int step_k = 4 * (32 / bits);
   const size_t max_splits = size_t(K) / (2 * step_k);
   const size_t capacity = size_t(148) * 6 * 4;
-  size_t splits = 3 * capacity / size_t(N / 32) + 1;
+  size_t splits = capacity / size_t(N / 32) + 1;
   if (splits > max_splits) splits = max_splits;
   if (g_decode_tuning.split_k > 0) splits = max_splits;
   return size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(N / 32) * splits * mrows * 32 * sizeof(float);

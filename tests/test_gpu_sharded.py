@@ -1,0 +1,53 @@
+"""GPU, >= 2 B200s: N-sharded op + NCCL all-gather equals the single-GPU op bit for bit (skipped on a 1-GPU box)."""
+
+from __future__ import annotations
+
+import os
+import pathlib
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def _worker(rank: int, world: int, port: int, ret) -> None:
+    import torch.distributed as dist
+
+    for p in (ROOT, ROOT / "oracle"):
+        sys.path.insert(0, str(p))
+    import mpgemm_oracle as oracle
+    from conch_b200.ops.quantization.gemm import mixed_precision_gemm
+    from conch_b200.sharded import ShardedMixedPrecisionLinear
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        for m in (1, 16, 200):
+            p = oracle.make_problem(m, 1024, 512, "uint4", 128, torch.float16, True, seed=m)
+            x, wq, ws, wzp = (t.cuda() for t in (p.x, p.w_q_packed, p.w_s, p.w_zp))
+            single = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128)
+            layer = ShardedMixedPrecisionLinear(wq, ws, wzp, 4, 0, 128)
+            out = layer(x)
+            torch.cuda.synchronize()
+            assert out.shape == single.shape
+            assert torch.equal(out, single), f"sharded != single at M={m}"
+            want = oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, 4, 0, 128)
+            torch.testing.assert_close(out.cpu().float(), want.float(), rtol=1e-2, atol=1e-2)
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_matches_single_gpu_nccl():
+    import torch.multiprocessing as mp
+
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, 29731, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
