@@ -168,6 +168,85 @@ __global__ void fill_random(unsigned* p, size_t n, unsigned seed) {
   }
 }
 
+template <bool FX, bool FM, bool FP>
+__global__ void __launch_bounds__(128, 5) kreal(const uint32_t* __restrict__ wq, const __half* __restrict__ xg, const __half* __restrict__ sg,
+                                             const int* __restrict__ zg, int N, int S, int nunits, int total_warps, float* part,
+                                             unsigned* cnt, __half* out) {
+  const int lane = threadIdx.x & 31, g8 = lane >> 2, tig = lane & 3;
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= total_warps) return;
+  const int cb = w / S, si = w - cb * S;
+  const int col = cb * 32 + 4 * g8;
+  const int b0 = si * nunits;
+  const char* p = reinterpret_cast<const char*>(wq + (size_t(b0) * 16 + tig) * N + col);
+  const size_t step_bytes = size_t(16) * N;
+  const int nsteps = nunits * 4;
+  uint4 win[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { win[j] = make_uint4(0, 0, 0, 0); if (j < nsteps) win[j] = ldg_na(p + j * step_bytes); }
+  p += 8 * step_bytes;
+  const __half* sp = sg + size_t(b0) * N + col;
+  const int* zp = zg + size_t(b0) * N + col;
+  uint2 raw_s = make_uint2(0x1C001C00u, 0x1C001C00u);
+  uint4 raw_z = make_uint4(8, 8, 8, 8);
+  if (FM) { raw_s = __ldg(reinterpret_cast<const uint2*>(sp)); raw_z = __ldg(reinterpret_cast<const uint4*>(zp)); sp += N; zp += N; }
+  const __half* xp = xg + tig * 8 + size_t(b0) * 128;
+  uint4 xnext = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+  const bool m_ok = g8 < 1;
+  if (FX && m_ok) xnext = __ldg(reinterpret_cast<const uint4*>(xp));
+  xp += 32;
+  float acc[2][4] = {};
+  cb200::ColQ cq[4];
+  for (int i = 0; i < nunits; ++i) {
+    {
+      __half s4[4]; *reinterpret_cast<uint2*>(s4) = raw_s;
+      const int z[4] = {int(raw_z.x), int(raw_z.y), int(raw_z.z), int(raw_z.w)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cq[j] = cb200::make_colq<__half, 4, cb200::Order::Lop, false>(s4[j], float(z[j]), __half(0.f));
+      if (FM && i + 1 < nunits) { raw_s = __ldg(reinterpret_cast<const uint2*>(sp)); raw_z = __ldg(reinterpret_cast<const uint4*>(zp)); sp += N; zp += N; }
+    }
+    const int h = i & 1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint4 wv;
+      if (h == 0) { wv = win[u]; if (i * 4 + u + 8 < nsteps) win[u] = ldg_na(p + u * step_bytes); }
+      else        { wv = win[4 + u]; if (i * 4 + u + 8 < nsteps) win[4 + u] = ldg_na(p + (4 + u) * step_bytes); }
+      uint32_t xb[4];
+      xb[0] = __byte_perm(xnext.x, xnext.z, 0x5410); xb[1] = __byte_perm(xnext.x, xnext.z, 0x7632);
+      xb[2] = __byte_perm(xnext.y, xnext.w, 0x5410); xb[3] = __byte_perm(xnext.y, xnext.w, 0x7632);
+      if (FX && m_ok && i * 4 + u + 1 < nsteps) xnext = __ldg(reinterpret_cast<const uint4*>(xp));
+      xp += 32;
+      const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t e[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cb200::dequant_word<__half, 4, cb200::Order::Lop, false>(words[j], cq[j], e[j]);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mma(acc[t], e[2 * t][0], e[2 * t + 1][0], e[2 * t][1], e[2 * t + 1][1], xb[0], xb[1]);
+        mma(acc[t], e[2 * t][2], e[2 * t + 1][2], e[2 * t][3], e[2 * t + 1][3], xb[2], xb[3]);
+      }
+    }
+    if (h == 1) p += 8 * step_bytes;
+  }
+  if (!FP) {
+    if (tig == 0) { out[col] = __float2half(acc[0][0]); out[col + 1] = __float2half(acc[0][2]); out[col + 2] = __float2half(acc[1][0]); out[col + 3] = __float2half(acc[1][2]); }
+    return;
+  }
+  float* mine = part + (size_t(cb) * S + si) * 32;
+  if (tig == 0) { __stcg(mine + 4 * g8, acc[0][0]); __stcg(mine + 4 * g8 + 1, acc[0][2]); __stcg(mine + 4 * g8 + 2, acc[1][0]); __stcg(mine + 4 * g8 + 3, acc[1][2]); }
+  __threadfence();
+  __syncwarp();
+  unsigned prev = 0;
+  if (lane == 0) prev = atomicAdd(cnt + cb, 1u);
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev != unsigned(S - 1)) return;
+  __threadfence();
+  float v = 0.f;
+  for (int s2 = 0; s2 < S; ++s2) v += __ldcg(part + (size_t(cb) * S + s2) * 32 + lane);
+  out[cb * 32 + lane] = __float2half(v);
+  if (lane == 0) cnt[cb] = 0u;
+}
+
 int main(int argc, char** argv) {
   const int R = argc > 1 ? atoi(argv[1]) : 512, N = argc > 2 ? atoi(argv[2]) : 28672;
   const size_t bytes = size_t(R) * N * 4;
@@ -192,7 +271,34 @@ int main(int argc, char** argv) {
     const double us = ms * 1e3 / (reps * copies);
     printf("%-34s S=%2d warps=%5d units/warp=%3d: %7.2f us %7.1f GB/s (%s)\n", name, S, warps, nunits, us, bytes / us / 1e3, cudaGetErrorString(cudaGetLastError()));
   };
-  for (int S : {1, 2, 4, 8}) {
+  {
+    __half *xg, *sg, *og; int* zg; float* part; unsigned* cnt;
+    cudaMalloc(&xg, 65536); cudaMemset(xg, 0x3c, 65536);
+    cudaMalloc(&sg, size_t(B) * N * 2); cudaMemset(sg, 0x1c, size_t(B) * N * 2);
+    cudaMalloc(&zg, size_t(B) * N * 4); cudaMemset(zg, 0, size_t(B) * N * 4);
+    cudaMalloc(&og, size_t(N) * 2); cudaMalloc(&part, size_t(N) * 64 * 4); cudaMalloc(&cnt, 65536); cudaMemset(cnt, 0, 65536);
+    auto runreal = [&](auto kern, const char* name, int S) {
+      const int nunits = B / S, warps = col_blocks * S, blocks = (warps + 3) / 4;
+      for (int i = 0; i < copies; ++i) kern<<<blocks, 128>>>(bufs[i], xg, sg, zg, N, S, nunits, warps, part, cnt, og);
+      cudaDeviceSynchronize();
+      const int reps = 5;
+      cudaEventRecord(e0);
+      for (int r = 0; r < reps; ++r) for (int i = 0; i < copies; ++i) kern<<<blocks, 128>>>(bufs[i], xg, sg, zg, N, S, nunits, warps, part, cnt, og);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      const double us = ms * 1e3 / (reps * copies);
+      printf("%-34s S=%2d warps=%5d units/warp=%3d: %7.2f us %7.1f GB/s (%s)\n", name, S, warps, nunits, us, bytes / us / 1e3, cudaGetErrorString(cudaGetLastError()));
+    };
+    for (int S : {2, 4, 8, 16}) {
+      if (B % S) continue;
+      runreal(kreal<false, false, false>, "real: window+dequant+4HMMA", S);
+      runreal(kreal<true, false, false>, "real: + x loads", S);
+      runreal(kreal<false, true, false>, "real: + per-group meta", S);
+      runreal(kreal<false, false, true>, "real: + split-K publish", S);
+      runreal(kreal<true, true, true>, "real: all", S);
+    }
+  }
+  for (int S : {4, 8}) {
     if (B % S) continue;
     run(k<0, 0, 1>, "regs dbuf, xor", S, 1, 0);
     run(k<0, 1, 1>, "regs dbuf, lop3", S, 1, 0);

@@ -9,8 +9,11 @@
 //     soon as it has been read -- so with ~24 resident warps per SM about 100 KB per SM is outstanding, which is what it
 //     takes to approach the HBM peak (measured: benchmarks/micro/stream_pattern.cu).  cp.async was measured and
 //     rejected: with 4 row segments per instruction LDGSTS serialises into 32 shared-memory wavefronts
-//     (benchmarks/micro/decode_steps.cu).  The activations (16 B per lane per step) come through L1, prefetched one step
-//     ahead; scales / zero-points are prefetched one group ahead in registers and several groups ahead into L2.
+//     (benchmarks/micro/decode_steps.cu).  NOTHING else may go through the load/store queue: loads return in issue
+//     order, so an L1-hit activation load queued behind DRAM-missing weight loads stalls the step for a full DRAM
+//     latency (measured: +8..16 us on a 58.7 MB layer, profiles/r01_micro_decode_features.log).  The warp's slice of
+//     x and its scale / zero-point rows are therefore fetched ONCE, at kernel start, by TMA bulk copies
+//     (cp.async.bulk -> per-warp shared memory, mbarrier completion) and read back with ld.shared.
 //     All cursors are linear pointer increments;
 //   * FUSED=false: nibbles are unpacked and W = (q - bias - zp) * s is formed per weight with dequant_word() -- the
 //     same bits as the dequant kernel and the reference's w_ref -- before the MMA;
@@ -47,6 +50,10 @@ struct DecodeGeom {
   int total_warps;    // (N / 32) * S
   int bpg;            // batches per scale group (g / (U * STEP_K))
   int pdl;            // launched with programmatic stream serialization
+  int x_row_bytes;    // per-warp smem: bytes per staged x row (slab bytes + 64 B pad against bank conflicts)
+  int meta_row_bytes; // per-warp smem: bytes per group row (64 B of scales + zero-points)
+  int ngroups;        // scale groups touched by one warp
+  int warp_smem;      // per-warp smem bytes (x rows + group rows + mbarrier)
 };
 
 template <class A>
@@ -65,7 +72,21 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const float (&c)[4], uin
   }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 
 // A: activation type, BITS: 4|8, MT: 8-row m tiles (1: M<=8, 2: M<=16), U: steps per batch (group boundaries fall on
 // batch boundaries), ZK: cb200_zp_kind (compile time), FUSED: feed magic-number operands to the MMA (see above).
@@ -108,67 +129,61 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   }
   wp += WIN * step_bytes;  // next load of slot j: wp + j * step_bytes
 
-  // ---- scales / zero-points: raw values of the NEXT group live in registers, converted when that group starts ----------
+  // ---- per-warp shared memory: x slab [m_rows][x_row_bytes], group rows [ngroups][meta_row_bytes], one mbarrier -------------
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t wsm = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) + (threadIdx.x >> 5) * geo.warp_smem;
+  const uint32_t xs_base = wsm;
+  const uint32_t meta_base = wsm + M * geo.x_row_bytes;
+  const uint32_t bar = meta_base + geo.ngroups * geo.meta_row_bytes;
   const int g0 = b0 / bpg;  // a slab either covers whole groups or lies inside one group
-  const int ngroups_mine = (nunits + bpg - 1) / bpg;
-  const A* sptr = reinterpret_cast<const A*>(p.s) + size_t(g0) * N + col;
-  const char* zptr = nullptr;
-  size_t z_row_bytes = 0;
-  if (zp_per_group) {
-    const size_t zes = ZK == CB200_ZP_I32 ? 4 : ZK == CB200_ZP_U8 ? 1 : 2;
-    zptr = reinterpret_cast<const char*>(p.zp) + (size_t(g0) * N + col) * zes;
-    z_row_bytes = size_t(N) * zes;
+  const int slab_k = nsteps * 4 * PF;
+  constexpr uint32_t ZROW = ZK == CB200_ZP_I32 ? 128u : ZK == CB200_ZP_U8 ? 32u : ZK == CB200_ZP_ACT ? 64u : 0u;  // 32 columns
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t total = uint32_t(M) * uint32_t(slab_k * 2) + uint32_t(geo.ngroups) * (64u + (zp_per_group ? ZROW : 0u));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
   }
-  uint2 raw_s = make_uint2(0u, 0u);
-  uint4 raw_z = make_uint4(0u, 0u, 0u, 0u);
-  auto fetch_meta = [&]() {  // loads only: nothing here may depend on the loaded values
-    raw_s = __ldg(reinterpret_cast<const uint2*>(sptr));
-    sptr += N;
-    if (zp_per_group) {
-      if constexpr (ZK == CB200_ZP_I32) raw_z = __ldg(reinterpret_cast<const uint4*>(zptr));
-      if constexpr (ZK == CB200_ZP_U8) raw_z.x = __ldg(reinterpret_cast<const uint32_t*>(zptr));
-      if constexpr (ZK == CB200_ZP_ACT) {
-        const uint2 t = __ldg(reinterpret_cast<const uint2*>(zptr));
-        raw_z.x = t.x;
-        raw_z.y = t.y;
-      }
-      zptr += z_row_bytes;
-    }
+  __syncwarp();
+  auto bulk = [&](uint32_t dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
   };
-  fetch_meta();
-  int groups_fetched = 1;
-  if (tig == 0) {  // pull the next few groups' metadata rows into L2 (one lane per distinct address)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (j + 1 < ngroups_mine) {
-        prefetch_l2(sptr + size_t(j) * N);
-        if (zp_per_group) prefetch_l2(zptr + j * z_row_bytes);
-      }
+  // scales / zero-points of this warp's 32 columns, one row per group (static data: legal before griddepcontrol.wait)
+  for (int g = lane; g < geo.ngroups; g += 32) {
+    const size_t idx = size_t(g0 + g) * N + cb * CW;
+    bulk(meta_base + g * geo.meta_row_bytes, reinterpret_cast<const A*>(p.s) + idx, 64u);
+    if (zp_per_group) {
+      const size_t zes = ZK == CB200_ZP_I32 ? 4 : ZK == CB200_ZP_U8 ? 1 : 2;
+      bulk(meta_base + g * geo.meta_row_bytes + 64, reinterpret_cast<const char*>(p.zp) + idx * zes, ZROW);
     }
   }
 
   if (geo.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // x / out / workspace belong to the stream order
 
-  // ---- activations: one step prefetched ahead through L1 ---------------------------------------------------------------------
+  // activations: row m of x, columns [b0 * U * STEP_K, + slab_k), one bulk copy per row
+  if (lane < M) {
+    bulk(xs_base + lane * geo.x_row_bytes, reinterpret_cast<const A*>(p.x) + size_t(lane) * p.K + size_t(b0) * (U * 4 * PF),
+         uint32_t(slab_k * 2));
+  }
   bool m_ok[MT];
-  const A* xp[MT];
-  uint4 xnext[MT];
+  uint32_t lane_x[MT];  // + step * (4 * PF * 2)
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int m = mt * 8 + g8;
     m_ok[mt] = m < M;
-    xp[mt] = reinterpret_cast<const A*>(p.x) + size_t(m_ok[mt] ? m : 0) * p.K + tig * PF + size_t(b0) * (U * 4 * PF);
-    xnext[mt] = make_uint4(0u, 0u, 0u, 0u);
-    if (m_ok[mt]) {
-      if constexpr (BITS == 4) {
-        xnext[mt] = __ldg(reinterpret_cast<const uint4*>(xp[mt]));
-      } else {
-        const uint2 t = __ldg(reinterpret_cast<const uint2*>(xp[mt]));
-        xnext[mt].x = t.x;
-        xnext[mt].y = t.y;
-      }
+    lane_x[mt] = xs_base + (m_ok[mt] ? m : 0) * geo.x_row_bytes + tig * (PF * 2);
+  }
+  uint32_t meta_cur = meta_base;  // row of the current group
+  {  // wait for the staged operands (they landed long before the first weight load returns)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(bar)
+                   : "memory");
     }
-    xp[mt] += 4 * PF;
   }
 
   // ---- consume-side state ---------------------------------------------------------------------------------------------------
@@ -215,9 +230,9 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   // ---- one batch: U steps out of window slots [W0, W0 + U); `step` is the index of its first step ------------------------------
   auto process = [&](auto w0_tag, int step) {
     constexpr int W0 = decltype(w0_tag)::value;
-    if (refresh) {  // group boundary (warp-uniform): convert the prefetched raw metadata, prefetch the next group's
+    if (refresh) {  // group boundary (warp-uniform): this group's scales / zero-points from the staged rows
       A s4[VEC];
-      *reinterpret_cast<uint2*>(s4) = raw_s;
+      *reinterpret_cast<uint2*>(s4) = lds64(meta_cur + g8 * 8);
       float z[VEC];
       A zf[VEC];
 #pragma unroll
@@ -227,14 +242,17 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
       }
       if (zp_per_group) {
         if constexpr (ZK == CB200_ZP_I32) {
-          z[0] = float(int(raw_z.x)); z[1] = float(int(raw_z.y)); z[2] = float(int(raw_z.z)); z[3] = float(int(raw_z.w));
+          const uint4 zr = lds128(meta_cur + 64 + g8 * 16);
+          z[0] = float(int(zr.x)); z[1] = float(int(zr.y)); z[2] = float(int(zr.z)); z[3] = float(int(zr.w));
         } else if constexpr (ZK == CB200_ZP_U8) {
+          const uint32_t zr = lds32(meta_cur + 64 + g8 * 4);
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) z[j] = float((raw_z.x >> (8 * j)) & 0xffu);
+          for (int j = 0; j < VEC; ++j) z[j] = float((zr >> (8 * j)) & 0xffu);
         } else if constexpr (ZK == CB200_ZP_ACT) {
-          *reinterpret_cast<uint2*>(zf) = make_uint2(raw_z.x, raw_z.y);
+          *reinterpret_cast<uint2*>(zf) = lds64(meta_cur + 64 + g8 * 8);
         }
       }
+      meta_cur += geo.meta_row_bytes;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         if constexpr (FUSED) {
@@ -247,43 +265,29 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         }
       }
       refresh = false;
-      if (groups_fetched < ngroups_mine) {
-        if (tig == 0 && groups_fetched + 3 < ngroups_mine) {
-          prefetch_l2(sptr + size_t(3) * N);
-          if (zp_per_group) prefetch_l2(zptr + 3 * z_row_bytes);
-        }
-        fetch_meta();
-        ++groups_fetched;
-      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       // this step's weights leave the window; its slot is re-loaded with the step WIN ahead right away
       const uint4 wv = win[W0 + u];
       if (step + u + WIN < nsteps) win[W0 + u] = ldg_stream_v4(wp + (W0 + u) * step_bytes);
-      // activations of this step (prefetched), permuted to the lop3 nibble order; then prefetch the next step's
+      // activations of this step from the staged slab, permuted to the lop3 nibble order
       uint32_t xb[MT][PAIRS];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         if constexpr (BITS == 4) {
-          xb[mt][0] = __byte_perm(xnext[mt].x, xnext[mt].z, 0x5410);  // (k0,k4)
-          xb[mt][1] = __byte_perm(xnext[mt].x, xnext[mt].z, 0x7632);  // (k1,k5)
-          xb[mt][2] = __byte_perm(xnext[mt].y, xnext[mt].w, 0x5410);  // (k2,k6)
-          xb[mt][3] = __byte_perm(xnext[mt].y, xnext[mt].w, 0x7632);  // (k3,k7)
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (m_ok[mt]) v = lds128(lane_x[mt] + (step + u) * (4 * PF * 2));
+          xb[mt][0] = __byte_perm(v.x, v.z, 0x5410);  // (k0,k4)
+          xb[mt][1] = __byte_perm(v.x, v.z, 0x7632);  // (k1,k5)
+          xb[mt][2] = __byte_perm(v.y, v.w, 0x5410);  // (k2,k6)
+          xb[mt][3] = __byte_perm(v.y, v.w, 0x7632);  // (k3,k7)
         } else {
-          xb[mt][0] = xnext[mt].x;
-          xb[mt][1] = xnext[mt].y;
+          uint2 v = make_uint2(0u, 0u);
+          if (m_ok[mt]) v = lds64(lane_x[mt] + (step + u) * (4 * PF * 2));
+          xb[mt][0] = v.x;
+          xb[mt][1] = v.y;
         }
-        if (m_ok[mt] && step + u + 1 < nsteps) {
-          if constexpr (BITS == 4) {
-            xnext[mt] = __ldg(reinterpret_cast<const uint4*>(xp[mt]));
-          } else {
-            const uint2 t = __ldg(reinterpret_cast<const uint2*>(xp[mt]));
-            xnext[mt].x = t.x;
-            xnext[mt].y = t.y;
-          }
-        }
-        xp[mt] += 4 * PF;
       }
       const uint32_t words[VEC] = {wv.x, wv.y, wv.z, wv.w};
       uint32_t d[VEC][PAIRS];
@@ -432,11 +436,13 @@ struct DecodePlan {
   int bpg;             // batches per scale group
   int splits, units_per_warp, col_blocks, total_warps;
   int ctas_per_sm;
+  int x_row_bytes, meta_row_bytes, ngroups, warp_smem, max_units;
   bool fused;
 };
 
-// Every knob is overridable through cb200_set_decode_tuning(warps_n -> 1 (default): per-weight dequant before the MMA (W
-// bits identical to the reference's w_ref), 2: fused magic-number operands; warps_k -> CTAs per SM assumed resident;
+// Every knob is overridable through cb200_set_decode_tuning(warps_n -> 1: per-weight dequant before the MMA (W bits
+// identical to the reference's w_ref), 2 (default, measured 5-10% faster): fused magic-number operands; warps_k -> CTAs
+// per SM assumed resident;
 // split_k -> forced split count S (rounded down to a legal divisor); vec_words unused).
 static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
   DecodePlan pl;
@@ -445,42 +451,73 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
   const int B = K / (pl.u * step_k);  // batches per column block
   pl.bpg = g / (pl.u * step_k);
   pl.col_blocks = N / 32;
-  pl.fused = g_decode_tuning.warps_n == 2;
+  pl.fused = g_decode_tuning.warps_n != 1;
   // __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   pl.ctas_per_sm = pick(g_decode_tuning.warps_k, mrows > 8 ? 3 : (pl.fused ? 4 : 5));
-  const int capacity = 148 * pl.ctas_per_sm * 4;  // co-resident warps
+  const int by_regs = pl.ctas_per_sm;
+  const int zrow = 128;  // worst case (int32 zero-points) keeps the layout independent of the zero-point kind
+  auto warp_smem_for = [&](int per) {
+    const int xrow = per * pl.u * step_k * 2 + 64;
+    const int ng = (per + pl.bpg - 1) / pl.bpg;
+    return ((mrows * xrow + ng * (64 + zrow) + 8 + 127) / 128) * 128;
+  };
+  // per-warp staging budget bounds the slab: x rows (2 B per k per row) must fit ~8 KB (16 KB for the 16-row variant)
+  {
+    const int budget = mrows > 8 ? 16 * 1024 : 8 * 1024;
+    int mu = budget / (mrows * 2 * pl.u * step_k);
+    if (mu < 1) mu = 1;
+    pl.max_units = mu;
+  }
   // S must divide B, and a slab must not cut a group unless the group spans whole slabs (per-channel / huge groups):
-  // legal S: (B / S) % bpg == 0  or  bpg % (B / S) == 0.  Pick the largest legal S that keeps one wave and >= 2 batches.
+  // legal S: (B / S) % bpg == 0  or  bpg % (B / S) == 0.  Pick the largest legal S that keeps one co-resident wave.
   int best = 1;
+  bool best_ok = false;
   for (int sdiv = 1; sdiv <= B; ++sdiv) {
     if (B % sdiv) continue;
     const int per = B / sdiv;
     if (!(per % pl.bpg == 0 || pl.bpg % per == 0)) continue;
     if (g_decode_tuning.split_k > 0) {
-      if (sdiv <= g_decode_tuning.split_k) best = sdiv;
+      if (sdiv <= g_decode_tuning.split_k || per > pl.max_units) best = sdiv;
       continue;
     }
+    if (per > pl.max_units) {  // slab too long for the staging buffer: must split further
+      best = sdiv;
+      continue;
+    }
+    int by_smem = (227 * 1024) / (4 * warp_smem_for(per) + 1024);
+    if (by_smem > by_regs) by_smem = by_regs;
+    const int64_t capacity = int64_t(148) * by_smem * 4;  // co-resident warps at this split
     const int64_t warps = int64_t(pl.col_blocks) * sdiv;
-    if (warps > capacity && best > 0 && sdiv > 1) break;  // one co-resident wave (measured: more waves do not help)
-    if (per < 2 && sdiv > 1) break;
+    if (best_ok && warps > capacity && sdiv > 1) break;  // one co-resident wave (measured: more waves do not help)
+    if (best_ok && per < 2 && sdiv > 1) break;
     best = sdiv;
+    best_ok = true;
   }
   pl.splits = best;
   pl.units_per_warp = B / best;
   pl.total_warps = pl.col_blocks * best;
+  pl.x_row_bytes = pl.units_per_warp * pl.u * step_k * 2 + 64;
+  pl.meta_row_bytes = 64 + zrow;
+  pl.ngroups = (pl.units_per_warp + pl.bpg - 1) / pl.bpg;
+  pl.warp_smem = warp_smem_for(pl.units_per_warp);
   return pl;
 }
 
 size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits) {
-  const int mrows = int(M < 16 ? M : 16);
-  // the group size changes the plan through U and the legal splits; bound by the finest legal split (one batch per warp)
-  const int step_k = 4 * (32 / bits);
-  const size_t max_splits = size_t(K) / (2 * step_k);
-  const size_t capacity = size_t(148) * 6 * 4;
-  size_t splits = capacity / size_t(N / 32) + 1;
-  if (splits > max_splits) splits = max_splits;
-  if (g_decode_tuning.split_k > 0) splits = max_splits;
-  return size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(N / 32) * splits * mrows * 32 * sizeof(float);
+  // the group size changes the plan (U, legal splits): take the largest footprint over the group sizes the op accepts
+  size_t need = 0;
+  for (int rows : {int(M < 16 ? M : 16), int(M > 16 ? ((M - 1) % 16) + 1 : (M < 16 ? M : 16))}) {
+    for (int64_t g = 64; g <= K; g *= 2) {
+      if (K % g) continue;
+      const DecodePlan pl = decode_plan(rows, int(K), int(N), bits, int(g));
+      const size_t b = pl.splits > 1 ? size_t(pl.total_warps) * rows * 32 * sizeof(float) : 0;
+      need = b > need ? b : need;
+    }
+    const DecodePlan pk = decode_plan(rows, int(K), int(N), bits, int(K));
+    const size_t b = pk.splits > 1 ? size_t(pk.total_warps) * rows * 32 * sizeof(float) : 0;
+    need = b > need ? b : need;
+  }
+  return size_t(CB200_WORKSPACE_COUNTER_BYTES) + need;
 }
 
 template <class A, int BITS, int MT, int U, int ZK>
@@ -563,16 +600,20 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     geo.total_warps = pl.total_warps;
     geo.bpg = pl.bpg;
     geo.pdl = g_decode_pdl;
+    geo.x_row_bytes = pl.x_row_bytes;
+    geo.meta_row_bytes = pl.meta_row_bytes;
+    geo.ngroups = pl.ngroups;
+    geo.warp_smem = pl.warp_smem;
     const int blocks = (pl.total_warps + 3) / 4;
     float* wsp = ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES) : nullptr;
     unsigned* wsc = reinterpret_cast<unsigned*>(ws);
     int rc;
     if (act_dtype == CB200_F16) {
-      rc = bits == 4 ? launch_typed<__half, 4>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream)
-                     : launch_typed<__half, 8>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream);
+      rc = bits == 4 ? launch_typed<__half, 4>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream)
+                     : launch_typed<__half, 8>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream);
     } else {
-      rc = bits == 4 ? launch_typed<__nv_bfloat16, 4>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream)
-                     : launch_typed<__nv_bfloat16, 8>(pl.u, pl.fused, p, geo, blocks, 0, wsp, wsc, stream);
+      rc = bits == 4 ? launch_typed<__nv_bfloat16, 4>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream)
+                     : launch_typed<__nv_bfloat16, 8>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream);
     }
     if (rc != 0) return rc;
     if (launches) ++*launches;
