@@ -169,8 +169,11 @@ int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const v
 
   int chosen = variant;
   if (chosen == CB200_AUTO) {
-    // regime split: HBM-bound skinny GEMM up to 16 rows, tensor-core pipeline above
-    chosen = (M <= 16 || !tc_supported(p, weight_size_bits)) ? CB200_DECODE_MMA : CB200_TC_SS;
+    // regime split: HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x), tcgen05 pipeline above; 9..16 rows
+    // stay on the decode kernel only for big matrices, where its single launch beats the tcgen05 kernel's split-K
+    // pipeline (measured, profiles/r01_midm_probe.log)
+    const bool decode = M <= 8 || (M <= 16 && K * N > (int64_t(32) << 20));
+    chosen = (decode || !tc_supported(p, weight_size_bits)) ? CB200_DECODE_MMA : CB200_TC_TS;
   }
   int launches = 0;
   if (chosen == CB200_DECODE_MMA) {

@@ -8,15 +8,18 @@
 // (8 consecutive k of one column, conch/third_party/vllm/quant_utils.py:119-124) turns into one 16-byte K-major chunk,
 // (b) small M cheap (MMA-N = 16 instead of 112 wasted rows of a 128-row tile), (c) x a plain K-major TMA tile.
 //
-// Roles (384 threads):  warp 0 lane 0  TMA producer   (x tile, 128B-swizzled; packed W tile, 8|16 rows x 128 int32)
+// Roles (640 threads):  warp 0 lane 0  TMA producer   (x tile, 128B-swizzled; packed W tile, 8|16 rows x 128 int32)
 //                       warp 1 lane 0  MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=m_tile, K=16)
 //                       warp 2         TMEM allocator
-//                       warps 4..11    dequant        (smem packed -> registers -> dequant_word() -> operand A)
+//                       warps 4..19    dequant        (smem packed -> registers -> dequant_word() -> operand A): four
+//                                      SETS of four warps; set j owns stages j, j+4, ... (a thread = one weight column,
+//                                      all 64 k of the stage), so four stages are being dequantised concurrently and a
+//                                      set's barrier / shared-load / tcgen05.st latencies hide behind the other sets;
 //                                      then epilogue  (tcgen05.ld -> cast -> global)
 // Operand A (dequantised W) goes either to shared memory in the canonical K-major SWIZZLE_128B layout (variant SS) or
 // straight into tensor memory with tcgen05.st (variant TS: the weights never touch shared memory again, which halves
 // the smem traffic per MMA -- the limiter of this kernel).
-// Barriers per stage: full_x (TMA tx), full_w (TMA tx), a_ready (8 dequant warps), empty (tcgen05.commit).
+// Barriers per stage: full_x (TMA tx), full_w (TMA tx), a_ready (the 4 warps of one set), empty (tcgen05.commit).
 #include <cuda.h>
 
 #include <mutex>
@@ -111,6 +114,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -176,22 +189,30 @@ struct TcCfg {
   static constexpr int S_SMEM = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int S_TMEM = TS ? (512 - MT) / 32 : 8;
   static constexpr int S0 = S_SMEM < S_TMEM ? S_SMEM : S_TMEM;
-  static constexpr int S = S0 > 8 ? 8 : S0;
+  // The ring depth must be a multiple of the number of dequant sets (4): then ring slot s is always served by set
+  // s % 4, which therefore observes EVERY phase of that slot's full_w barrier in order.  (A set that skipped a phase
+  // could pass a parity wait one phase early -- mbarrier parity only distinguishes adjacent phases.)
+  static constexpr int S = S0 >= 8 ? 8 : 4;
   static constexpr int A_COL0 = MT;                     // first TMEM column of the A ring (TS)
   static constexpr int TMEM_NEED = MT + (TS ? S * 32 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = S * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
-  static_assert(S >= 2, "pipeline needs at least two stages");
+  static_assert(S0 >= 4, "pipeline needs at least four stages (one per dequant set)");
 };
 
+constexpr int kTcSets = 4;                       // dequant warp sets (4 warps each)
+constexpr int kTcThreads = 128 + 128 * kTcSets;  // 640
+
 template <class A, int BITS, int MT, bool TS, int ZK>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
     tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, TcParams prm) {
   using Cfg = TcCfg<MT, BITS, TS>;
   constexpr int S = Cfg::S;
   constexpr bool FZP = ZK == CB200_ZP_ACT;
   constexpr int PAIRS = 16 / BITS;     // pair registers per packed word
-  constexpr int WPT = 32 / Cfg::PF;    // packed words per dequant thread per stage (32 k of one column): 4 | 8
+  constexpr int WPT = 64 / Cfg::PF;    // packed words per dequant thread per stage (all 64 k of one column): 8 | 16
+  constexpr int SETS = kTcSets;
+  static_assert(Cfg::S % kTcSets == 0, "ring slot <-> dequant set mapping must be fixed (mbarrier phase order)");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -222,7 +243,7 @@ __global__ void __launch_bounds__(384, 1)
     for (int s = 0; s < S; ++s) {
       mbar_init(full_x(s), 1);
       mbar_init(full_w(s), 1);
-      mbar_init(a_ready(s), 8);
+      mbar_init(a_ready(s), 4);
       mbar_init(empty(s), 1);
     }
     mbar_init(d_full, 1);
@@ -277,26 +298,28 @@ __global__ void __launch_bounds__(384, 1)
     }
   } else if (warp >= 4) {
     // ================================ dequant warps, then epilogue ==================================================
-    const int q = warp & 3;          // TMEM lane quarter this warp may touch
-    const int kh = (warp - 4) >> 2;  // which 32-k half of the 64-k stage
-    const int nl = q * 32 + lane;    // weight column inside the tile == TMEM lane
+    const int q = warp & 3;            // TMEM lane quarter this warp may touch
+    const int set = (warp - 4) >> 2;   // this warp's set: owns stages set, set + SETS, ...
+    const int nl = q * 32 + lane;      // weight column inside the tile == TMEM lane
     const int n = n0 + nl;
     const bool n_ok = n < p.N;
     const A* sp = reinterpret_cast<const A*>(p.s);
-    const int bpg = p.g / Cfg::KB;   // 64-k blocks per group (g % 64 == 0)
-    const int ngrp = p.K / p.g;
     A raw_s = A(0.f), raw_zf = A(0.f);
     float raw_z = 0.f;
+    float zscalar = 0.f;
+    A zfscalar = A(0.f);
     if (ZK != CB200_ZP_NONE && p.zp_scalar) {
-      if constexpr (ZK == CB200_ZP_I32) raw_z = float(__ldg(reinterpret_cast<const int32_t*>(p.zp)));
-      if constexpr (ZK == CB200_ZP_U8) raw_z = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp)));
-      if constexpr (ZK == CB200_ZP_ACT) raw_zf = *reinterpret_cast<const A*>(p.zp);
+      if constexpr (ZK == CB200_ZP_I32) zscalar = float(__ldg(reinterpret_cast<const int32_t*>(p.zp)));
+      if constexpr (ZK == CB200_ZP_U8) zscalar = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp)));
+      if constexpr (ZK == CB200_ZP_ACT) zfscalar = *reinterpret_cast<const A*>(p.zp);
     }
     const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
-    auto fetch_group = [&](int grp) {
-      if (grp >= ngrp) grp = ngrp - 1;
-      if (!n_ok) return;
-      const size_t idx = size_t(grp) * p.N + n;
+    // scale / zero-point of this thread's column for the group of K block `kb` (one prefetch ahead, raw)
+    auto fetch_meta = [&](int kb) {
+      raw_z = zscalar;
+      raw_zf = zfscalar;
+      if (!n_ok || kb >= kb1) return;
+      const size_t idx = size_t((kb * Cfg::KB) / p.g) * p.N + n;
       raw_s = sp[idx];
       if (zp_per_group) {
         if constexpr (ZK == CB200_ZP_I32) raw_z = float(__ldg(reinterpret_cast<const int32_t*>(p.zp) + idx));
@@ -304,49 +327,37 @@ __global__ void __launch_bounds__(384, 1)
         if constexpr (ZK == CB200_ZP_ACT) raw_zf = reinterpret_cast<const A*>(p.zp)[idx];
       }
     };
-    int grp = (kb0 * Cfg::KB) / p.g;
-    int left = 0;
-    bool first = true;
-    const int first_left = (grp + 1) * bpg - kb0;
-    fetch_group(grp);
-    ColQ cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, raw_z + float(p.bias), raw_zf);
+    fetch_meta(kb0 + set);
 
-    for (int it = 0; it < nk; ++it) {
+    for (int it = set; it < nk; it += SETS) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
-      if (left == 0) {
-        cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, raw_z + float(p.bias), raw_zf);
-        left = first ? first_left : bpg;
-        first = false;
-        ++grp;
-        fetch_group(grp);
-      }
-      --left;
+      const ColQ cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, raw_z + float(p.bias), raw_zf);
+      fetch_meta(kb0 + it + SETS);  // for this set's next stage; consumed one full stage later
       mbar_wait(full_w(s), ph);
       const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem_gen + (w_base - smem_base) + s * Cfg::W_BYTES);
-      uint32_t regs[16];
+      uint32_t regs[32];
 #pragma unroll
       for (int j = 0; j < WPT; ++j) {
-        const uint32_t word = wst[(kh * WPT + j) * Cfg::NTILE + nl];
+        const uint32_t word = wst[j * Cfg::NTILE + nl];
         uint32_t pr[PAIRS];
         dequant_word<A, BITS, Order::Natural, FZP>(word, cq, pr);
 #pragma unroll
         for (int i = 0; i < PAIRS; ++i) regs[j * PAIRS + i] = pr[i];
       }
       if constexpr (TS) {
-        // lane nl of TMEM, columns [A_COL0 + 32 s + 16 kh, +16): 32 consecutive k of this column, 2 per 32-bit cell
-        tmem_st16(tmem_base + (uint32_t(q * 32) << 16) + Cfg::A_COL0 + s * 32 + kh * 16, regs);
+        // lane nl of TMEM, columns [A_COL0 + 32 s, +32): the 64 k of this column, 2 per 32-bit cell
+        tmem_st32(tmem_base + (uint32_t(q * 32) << 16) + Cfg::A_COL0 + s * 32, regs);
         tmem_st_wait();
         tc_fence_before();
       } else {
         // row nl of the K-major tile: 16-byte chunk c holds k = 8c..8c+7; 128B swizzle: chunk ^= row & 7
         const uint32_t row = a_base + s * Cfg::A_BYTES + nl * 128;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const uint32_t c = kh * 4 + c4;
-          const uint32_t addr = row + ((c ^ (nl & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(regs[c4 * 4 + 0]), "r"(regs[c4 * 4 + 1]),
-                       "r"(regs[c4 * 4 + 2]), "r"(regs[c4 * 4 + 3])
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t addr = row + ((uint32_t(c) ^ (nl & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(regs[c * 4 + 0]), "r"(regs[c * 4 + 1]),
+                       "r"(regs[c * 4 + 2]), "r"(regs[c * 4 + 3])
                        : "memory");
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
@@ -358,18 +369,18 @@ __global__ void __launch_bounds__(384, 1)
     // ---- epilogue: D^T[n, m] (lane = n, column = m) -> out[m, n] ------------------------------------------------------
     mbar_wait(d_full, 0);
     tc_fence_after();
-    constexpr int HALF = MT / 2;                     // columns (m) handled by this warp
-    constexpr int CH = HALF >= 32 ? 32 : HALF;       // columns per tcgen05.ld
+    constexpr int ESETS = MT >= 64 ? SETS : (MT / 16);  // sets taking part in the epilogue (>= 16 columns per warp)
+    constexpr int EC = MT / ESETS;                      // columns (m) handled by this warp
+    constexpr int CH = EC >= 32 ? 32 : EC;              // columns per tcgen05.ld
     const bool split = gridDim.z > 1;
     float* part = split ? prm.ws_partial + size_t(blockIdx.z) * p.M * p.N : nullptr;
 #pragma unroll 1
-    for (int cb = 0; cb < HALF; cb += CH) {
-      const int col0 = kh * HALF + cb;
+    for (int cb = 0; cb < (set < ESETS ? EC : 0); cb += CH) {
+      const int col0 = set * EC + cb;
       uint32_t r[32];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + col0;
       if constexpr (CH == 32) tmem_ld32(taddr, r);
       if constexpr (CH == 16) tmem_ld16(taddr, r);
-      if constexpr (CH == 8) tmem_ld8(taddr, r);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
@@ -377,7 +388,7 @@ __global__ void __launch_bounds__(384, 1)
         if (m < p.M && n_ok) {
           const float v = __uint_as_float(r[c]);
           if (split) {
-            part[size_t(m) * p.N + n] = v;
+            __stcg(part + size_t(m) * p.N + n, v);
           } else {
             store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, v);
           }
@@ -392,13 +403,21 @@ __global__ void __launch_bounds__(384, 1)
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-// out[m, n] = cast(sum_z partial[z][m][n])
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t total, int splits,
+// out[m, n] = cast(sum_z partial[z][m][n]) -- all SMs in parallel (measured faster than a last-CTA fix-up here: the
+// partial planes are M x N fp32, far more than one CTA can sum quickly)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t total4, int splits,
                                      int out_dtype) {
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    float v = 0.f;
-    for (int z = 0; z < splits; ++z) v += part[size_t(z) * total + i];
-    store_out<float>(out, out_dtype, size_t(i), v);
+  const float4* p4 = reinterpret_cast<const float4*>(part);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 v = __ldcg(p4 + i);
+    for (int z = 1; z < splits; ++z) {
+      const float4 t = __ldcg(p4 + size_t(z) * total4 + i);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    store_out<float>(out, out_dtype, size_t(4 * i + 0), v.x);
+    store_out<float>(out, out_dtype, size_t(4 * i + 1), v.y);
+    store_out<float>(out, out_dtype, size_t(4 * i + 2), v.z);
+    store_out<float>(out, out_dtype, size_t(4 * i + 3), v.w);
   }
 }
 
@@ -439,8 +458,8 @@ static TcPlan tc_plan(int M, int K, int N) {
   int ks = 1;
   if (g_tc_tuning.split_k > 0) {
     ks = g_tc_tuning.split_k;
-  } else if (tiles < 148) {
-    ks = (148 + tiles - 1) / tiles;          // aim for one wave of CTAs
+  } else if (tiles <= 74) {
+    ks = 148 / tiles;                         // exactly one wave of CTAs (never spill into a second one)
     while (ks > 1 && kblocks / ks < 4) --ks;  // keep at least four K blocks per CTA
   }
   if (ks > kblocks) ks = kblocks;
@@ -469,7 +488,7 @@ static int launch_cfg(const CUtensorMap& mx, const CUtensorMap& mw, const TcPara
     CB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(mx, mw, prm);
+  kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(mx, mw, prm);
   CB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -550,6 +569,7 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
     prm.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES);
   }
   dim3 grid((p.N + 127) / 128, (p.M + mt - 1) / mt, pl.split_k);
+
   const bool ts = variant != CB200_TC_SS;
   int rc;
   if (act_dtype == CB200_F16) {
@@ -564,10 +584,10 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
   if (rc) return rc;
   if (launches) ++*launches;
   if (pl.split_k > 1) {
-    const int64_t total = int64_t(p.M) * p.N;
-    int blocks = int((total + 255) / 256);
+    const int64_t total4 = int64_t(p.M) * p.N / 4;  // N % 64 == 0
+    int blocks = int((total4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(prm.ws_partial, p.out, total, pl.split_k, p.out_dtype);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(prm.ws_partial, p.out, total4, pl.split_k, p.out_dtype);
     CB200_CUDA_CHECK(cudaGetLastError());
     if (launches) ++*launches;
   }
