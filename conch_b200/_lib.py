@@ -32,6 +32,7 @@ EXPORTS = (
     "cb200_set_decode_tuning",
     "cb200_set_tc_tuning",
     "cb200_set_pdl",
+    "cb200_set_tc_cluster",
 )
 
 _lock = threading.Lock()
@@ -87,6 +88,8 @@ def load() -> ctypes.CDLL:
         lib.cb200_set_decode_tuning.argtypes = [c_int, c_int, c_int, c_int]
         lib.cb200_set_tc_tuning.restype = None
         lib.cb200_set_tc_tuning.argtypes = [c_int, c_int]
+        lib.cb200_set_tc_cluster.restype = None
+        lib.cb200_set_tc_cluster.argtypes = [c_int]
         lib.cb200_set_pdl.restype = None
         lib.cb200_set_pdl.argtypes = [c_int]
         _lib = lib

@@ -31,6 +31,7 @@ NVCC_FLAGS = [
     "-fPIC",
     "-Xcompiler",
     "-fvisibility=hidden",
+    *os.environ.get("CB200_NVCC_EXTRA", "").split(),  # e.g. -DCB200_TC_TRACE for benchmarks/tc_trace.py (debug only)
 ]
 
 

@@ -102,6 +102,7 @@ void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_word
   g_decode_tuning = {warps_n, warps_k, split_k, vec_words};
 }
 void cb200_set_tc_tuning(int m_tile, int split_k) { g_tc_tuning = {m_tile, split_k}; }
+void cb200_set_tc_cluster(int ctas) { g_tc_cluster = (ctas == 1 || ctas == 2 || ctas == 4) ? ctas : 0; }
 void cb200_set_pdl(int enable) { g_decode_pdl = enable ? 1 : 0; }
 
 size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_size_bits, int variant) {

@@ -57,6 +57,7 @@ struct TcTuning {
   int m_tile, split_k;
 };
 extern TcTuning g_tc_tuning;
+extern int g_tc_cluster;
 
 // ---- device helpers -----------------------------------------------------------------------------------
 template <class T>

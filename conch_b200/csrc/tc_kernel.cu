@@ -8,7 +8,8 @@
 // (8 consecutive k of one column, conch/third_party/vllm/quant_utils.py:119-124) turns into one 16-byte K-major chunk,
 // (b) small M cheap (MMA-N = 16 instead of 112 wasted rows of a 128-row tile), (c) x a plain K-major TMA tile.
 //
-// Roles (640 threads):  warp 0 lane 0  TMA producer   (x tile, 128B-swizzled; packed W tile, 8|16 rows x 128 int32)
+// Roles (640 threads):  warp 0 lane 0  TMA producer   (packed W tile, 8|16 rows x 128 int32, deep ring)
+//                       warp 3 lane 0  TMA producer   (x tile, 128B-swizzled; multicast across a cluster if enabled)
 //                       warp 1 lane 0  MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=m_tile, K=16)
 //                       warp 2         TMEM allocator
 //                       warps 4..19    dequant        (smem packed -> registers -> dequant_word() -> operand A): four
@@ -19,7 +20,8 @@
 // Operand A (dequantised W) goes either to shared memory in the canonical K-major SWIZZLE_128B layout (variant SS) or
 // straight into tensor memory with tcgen05.st (variant TS: the weights never touch shared memory again, which halves
 // the smem traffic per MMA -- the limiter of this kernel).
-// Barriers per stage: full_x (TMA tx), full_w (TMA tx), a_ready (the 4 warps of one set), empty (tcgen05.commit).
+// Barriers: x ring x_full (TMA tx); W ring w_full (TMA tx) / w_free (the 4 warps of a set); A ring a_ready (the 4 warps
+// of a set) / mma_done (tcgen05.commit: releases the A slot AND the x slot of that K block); d_full.
 #include <cuda.h>
 
 #include <mutex>
@@ -30,6 +32,11 @@
 namespace cb200 {
 
 TcTuning g_tc_tuning = {0, 0};
+int g_tc_cluster = 0;  // 0 = heuristic
+#ifdef CB200_TC_TRACE
+long long* g_tc_trace = nullptr;
+extern "C" __attribute__((visibility("default"))) void cb200_debug_set_tc_trace(void* p) { g_tc_trace = reinterpret_cast<long long*>(p); }
+#endif
 
 // ------------------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -41,6 +48,17 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -69,6 +87,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
       "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+// same, delivered to every CTA of the cluster whose bit is set in `mask` (same smem offset, same barrier offset in each)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // .aligned: the whole warp must arrive together (role code above is lane-divergent)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -105,6 +140,12 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -173,6 +214,10 @@ struct TcParams {
   int kblocks_total;   // K / 64
   int kb_per_split;    // 64-wide K blocks per CTA along gridDim.z
   float* ws_partial;   // [split][M][N] fp32 when gridDim.z > 1
+  int cluster;         // CTAs per cluster along n (1, 2 or 4): they share one x tile through TMA multicast
+#ifdef CB200_TC_TRACE
+  long long* trace;    // [K/64][16] clock64 stamps of CTA (0,0,0) (debug builds only)
+#endif
 };
 
 template <int MT, int BITS, bool TS>
@@ -184,20 +229,26 @@ struct TcCfg {
   static constexpr int X_BYTES = MT * 128;              // MT rows x 64 halfs, 128B swizzle
   static constexpr int W_BYTES = WROWS * NTILE * 4;
   static constexpr int A_BYTES = TS ? 0 : NTILE * 128;  // dequantised W tile, K-major 128B swizzle
-  static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + A_BYTES;
   static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
-  static constexpr int S_SMEM = SMEM_BUDGET / STAGE_BYTES;
-  static constexpr int S_TMEM = TS ? (512 - MT) / 32 : 8;
-  static constexpr int S0 = S_SMEM < S_TMEM ? S_SMEM : S_TMEM;
-  // The ring depth must be a multiple of the number of dequant sets (4): then ring slot s is always served by set
-  // s % 4, which therefore observes EVERY phase of that slot's full_w barrier in order.  (A set that skipped a phase
-  // could pass a parity wait one phase early -- mbarrier parity only distinguishes adjacent phases.)
-  static constexpr int S = S0 >= 8 ? 8 : 4;
+  // Three independent rings (a slot is released as soon as ITS consumer is done with it, not when the MMA retires):
+  //   W ring  (packed weights, 4-8 KB per slot): TMA -> dequant warps; deep, it hides the HBM latency of the weights
+  //   A ring  (dequantised tile: 32 TMEM columns per slot, or 16 KB of shared memory in SS mode): dequant -> MMA
+  //   x ring  (activation tile, MT x 128 B per slot): TMA -> MMA
+  // SW and SA must be multiples of the number of dequant sets (4): then slot s is always served by set s % 4, which
+  // therefore observes EVERY phase of that slot's barriers in order.  (A set that skipped a phase could pass a parity
+  // wait one phase early -- mbarrier parity only distinguishes adjacent phases.)  The x ring is only touched by
+  // single threads that visit every iteration, so any depth <= SA works (its slots are released by the same
+  // tcgen05.commit as the A slots: ONE commit per K block keeps the MMA issue loop short).
+  static constexpr int SW = BITS == 4 ? (MT <= 128 ? 16 : 8) : (MT <= 128 ? 8 : 4);
+  static constexpr int SA = TS ? 8 : 4;
+  static constexpr int SX_FIT = (SMEM_BUDGET - SW * W_BYTES - SA * A_BYTES) / X_BYTES;
+  static constexpr int SX = SX_FIT > SA ? SA : SX_FIT;   // <= SA: the x producer reuses the A ring's mma_done barriers
   static constexpr int A_COL0 = MT;                     // first TMEM column of the A ring (TS)
-  static constexpr int TMEM_NEED = MT + (TS ? S * 32 : 0);
+  static constexpr int TMEM_NEED = MT + (TS ? SA * 32 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = S * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
-  static_assert(S0 >= 4, "pipeline needs at least four stages (one per dequant set)");
+  static constexpr int SMEM_BYTES = SX * X_BYTES + SW * W_BYTES + SA * A_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers*/;
+  static_assert(SX >= 3, "x ring too shallow");
+  static_assert(TMEM_NEED <= 512, "TMEM over-subscribed");
 };
 
 constexpr int kTcSets = 4;                       // dequant warp sets (4 warps each)
@@ -207,25 +258,26 @@ template <class A, int BITS, int MT, bool TS, int ZK>
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, TcParams prm) {
   using Cfg = TcCfg<MT, BITS, TS>;
-  constexpr int S = Cfg::S;
+  constexpr int SX = Cfg::SX, SW = Cfg::SW, SA = Cfg::SA;
   constexpr bool FZP = ZK == CB200_ZP_ACT;
   constexpr int PAIRS = 16 / BITS;     // pair registers per packed word
   constexpr int WPT = 64 / Cfg::PF;    // packed words per dequant thread per stage (all 64 k of one column): 8 | 16
   constexpr int SETS = kTcSets;
-  static_assert(Cfg::S % kTcSets == 0, "ring slot <-> dequant set mapping must be fixed (mbarrier phase order)");
+  static_assert(SW % kTcSets == 0 && SA % kTcSets == 0, "ring slot <-> dequant set mapping must be fixed (mbarrier phase order)");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_base = smem_base;
-  const uint32_t a_base = x_base + S * Cfg::X_BYTES;
-  const uint32_t w_base = a_base + S * Cfg::A_BYTES;
-  const uint32_t bar_base = w_base + S * Cfg::W_BYTES;
-  auto full_x = [&](int s) { return bar_base + 8u * s; };
-  auto full_w = [&](int s) { return bar_base + 8u * (S + s); };
-  auto a_ready = [&](int s) { return bar_base + 8u * (2 * S + s); };
-  auto empty = [&](int s) { return bar_base + 8u * (3 * S + s); };
-  const uint32_t d_full = bar_base + 8u * (4 * S);
-  const uint32_t tmem_slot = bar_base + 8u * (4 * S + 1);
+  const uint32_t a_base = x_base + SX * Cfg::X_BYTES;
+  const uint32_t w_base = a_base + SA * Cfg::A_BYTES;
+  const uint32_t bar_base = w_base + SW * Cfg::W_BYTES;
+  auto x_full = [&](int s) { return bar_base + 8u * s; };
+  auto w_full = [&](int s) { return bar_base + 8u * (SX + s); };
+  auto w_free = [&](int s) { return bar_base + 8u * (SX + SW + s); };
+  auto a_ready = [&](int s) { return bar_base + 8u * (SX + 2 * SW + s); };
+  auto mma_done = [&](int s) { return bar_base + 8u * (SX + 2 * SW + SA + s); };  // frees A slot s and its x slot
+  const uint32_t d_full = bar_base + 8u * (SX + 2 * SW + 2 * SA);
+  const uint32_t tmem_slot = d_full + 8u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
 
   const Problem& p = prm.p;
@@ -240,61 +292,109 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_x);
     prefetch_tensormap(&tmap_w);
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_x(s), 1);
-      mbar_init(full_w(s), 1);
+    for (int s = 0; s < SX; ++s) {
+      mbar_init(x_full(s), 1);
+    }
+    for (int s = 0; s < SW; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_free(s), 4);  // the four warps of the owning set
+    }
+    for (int s = 0; s < SA; ++s) {
       mbar_init(a_ready(s), 4);
-      mbar_init(empty(s), 1);
+      mbar_init(mma_done(s), prm.cluster);  // every CTA of the cluster must have released the x slot (x is multicast)
     }
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (prm.cluster > 1) {
+    cluster_sync_all();  // peers multicast into this CTA's shared memory and barriers: they must be initialised first
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
+  const uint32_t crank = prm.cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = uint16_t((1u << prm.cluster) - 1u);
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+#ifdef CB200_TC_TRACE
+  const bool tracing = prm.trace && blockIdx.x == 7 && blockIdx.y == 1 && blockIdx.z == 0;
+#define TRACE(slot, it) do { if (tracing) prm.trace[(it) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot, it) do { } while (0)
+#endif
 
   if (warp == 0) {
-    // ================================ TMA producer =================================================================
+    // ================================ TMA producer: packed weights ==================================================
     if (lane == 0) {
       for (int it = 0; it < nk; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(empty(s), ph ^ 1);
-        mbar_expect_tx(full_w(s), Cfg::W_BYTES);
-        tma_load_2d(w_base + s * Cfg::W_BYTES, &tmap_w, n0, (kb0 + it) * Cfg::WROWS, full_w(s));
-        mbar_expect_tx(full_x(s), Cfg::X_BYTES);
-        tma_load_2d(x_base + s * Cfg::X_BYTES, &tmap_x, (kb0 + it) * Cfg::KB, m0, full_x(s));
+        const int s = it % SW;
+        mbar_wait(w_free(s), ((it / SW) & 1) ^ 1);
+        TRACE(0, it);
+        mbar_expect_tx(w_full(s), Cfg::W_BYTES);
+        tma_load_2d(w_base + s * Cfg::W_BYTES, &tmap_w, n0, (kb0 + it) * Cfg::WROWS, w_full(s));
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ TMA producer: activations =====================================================
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % SX;
+        if (it >= SX) {  // slot last read by the MMAs of K block it - SX
+          const int j = it - SX;
+          mbar_wait(mma_done(j % SA), (j / SA) & 1);
+        }
+        TRACE(1, it);
+        mbar_expect_tx(x_full(s), Cfg::X_BYTES);
+        if (prm.cluster > 1) {
+          // this CTA fetches rows [crank * MT/cluster, +MT/cluster) of the shared x tile and multicasts them to all
+          const uint32_t rows = MT / prm.cluster;
+          tma_load_2d_mc(x_base + s * Cfg::X_BYTES + crank * rows * 128, &tmap_x, (kb0 + it) * Cfg::KB, m0 + int(crank * rows),
+                         x_full(s), cmask);
+        } else {
+          tma_load_2d(x_base + s * Cfg::X_BYTES, &tmap_x, (kb0 + it) * Cfg::KB, m0, x_full(s));
+        }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================================================
-    if (lane == 0) {
-      constexpr uint32_t fmt = std::is_same<A, __half>::value ? 0u : 1u;  // F16 / BF16
-      // instruction descriptor: D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major (bits 15,16 = 0),
-      // N>>3 at [17,23), M>>4 at [24,29)
-      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(MT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(full_x(s), ph);
-        mbar_wait(a_ready(s), ph);
-        tc_fence_after();
-        const uint64_t bdesc = make_sw128_desc(x_base + s * Cfg::X_BYTES);
+    // The whole warp runs the loop convergently and ONE elected lane issues: with `elect.sync` the compiler emits
+    // straight-line UTCHMMA code (a plain `lane == 0` branch makes it wrap every tcgen05 instruction in a
+    // per-active-thread uniformisation loop, which made this issue loop -- not the tensor pipe -- the limiter).
+    constexpr uint32_t fmt = std::is_same<A, __half>::value ? 0u : 1u;  // F16 / BF16
+    // instruction descriptor: D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major (bits 15,16 = 0),
+    // N>>3 at [17,23), M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(MT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    for (int it = 0; it < nk; ++it) {
+      const int sx = it % SX, sa = it % SA;
+      TRACE(2, it);
+      mbar_wait(x_full(sx), (it / SX) & 1);
+      TRACE(3, it);
+      mbar_wait(a_ready(sa), (it / SA) & 1);
+      TRACE(4, it);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bdesc = make_sw128_desc(x_base + sx * Cfg::X_BYTES);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {  // four K=16 MMAs per 64-wide stage: +32 bytes inside the swizzle atom
           const uint32_t acc = (it | k4) != 0;
           if constexpr (TS) {
-            umma_ts(tmem_base, tmem_base + Cfg::A_COL0 + s * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
+            umma_ts(tmem_base, tmem_base + Cfg::A_COL0 + sa * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
           } else {
-            const uint64_t adesc = make_sw128_desc(a_base + s * Cfg::A_BYTES);
+            const uint64_t adesc = make_sw128_desc(a_base + sa * Cfg::A_BYTES);
             umma_ss(tmem_base, adesc + uint64_t(k4 * 2), bdesc + uint64_t(k4 * 2), idesc, acc);
           }
         }
-        umma_commit(empty(s));  // frees x / packed-W / A slot s once these MMAs have read them
+        // once these MMAs have read them: release the A slot, and the x slot in every CTA that multicasts into it
+        if (prm.cluster > 1) {
+          umma_commit_mc(mma_done(sa), cmask);
+        } else {
+          umma_commit(mma_done(sa));
+        }
+        if (it == nk - 1) umma_commit(d_full);
       }
-      umma_commit(d_full);
+      __syncwarp();
+      TRACE(5, it);
     }
   } else if (warp >= 4) {
     // ================================ dequant warps, then epilogue ==================================================
@@ -330,12 +430,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     fetch_meta(kb0 + set);
 
     for (int it = set; it < nk; it += SETS) {
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
+      const int sw = it % SW, sa = it % SA;
       const ColQ cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, raw_z + float(p.bias), raw_zf);
+      if (q == 0 && lane == 0) TRACE(6, it);
       fetch_meta(kb0 + it + SETS);  // for this set's next stage; consumed one full stage later
-      mbar_wait(full_w(s), ph);
-      const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem_gen + (w_base - smem_base) + s * Cfg::W_BYTES);
+      if (q == 0 && lane == 0) TRACE(7, it);
+      mbar_wait(w_full(sw), (it / SW) & 1);
+      if (q == 0 && lane == 0) TRACE(8, it);
+      const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem_gen + (w_base - smem_base) + sw * Cfg::W_BYTES);
       uint32_t regs[32];
 #pragma unroll
       for (int j = 0; j < WPT; ++j) {
@@ -345,14 +447,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
         for (int i = 0; i < PAIRS; ++i) regs[j * PAIRS + i] = pr[i];
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_free(sw));  // the packed tile is in registers: the producer may refill the slot
+      if (q == 0 && lane == 0) TRACE(9, it);
+      mbar_wait(mma_done(sa), ((it / SA) & 1) ^ 1);
+      if (q == 0 && lane == 0) TRACE(10, it);
+      tc_fence_after();
       if constexpr (TS) {
-        // lane nl of TMEM, columns [A_COL0 + 32 s, +32): the 64 k of this column, 2 per 32-bit cell
-        tmem_st32(tmem_base + (uint32_t(q * 32) << 16) + Cfg::A_COL0 + s * 32, regs);
+        // lane nl of TMEM, columns [A_COL0 + 32 sa, +32): the 64 k of this column, 2 per 32-bit cell
+        tmem_st32(tmem_base + (uint32_t(q * 32) << 16) + Cfg::A_COL0 + sa * 32, regs);
         tmem_st_wait();
         tc_fence_before();
       } else {
         // row nl of the K-major tile: 16-byte chunk c holds k = 8c..8c+7; 128B swizzle: chunk ^= row & 7
-        const uint32_t row = a_base + s * Cfg::A_BYTES + nl * 128;
+        const uint32_t row = a_base + sa * Cfg::A_BYTES + nl * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t addr = row + ((uint32_t(c) ^ (nl & 7)) << 4);
@@ -363,7 +471,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready(s));
+      if (lane == 0) mbar_arrive(a_ready(sa));
+      if (q == 0 && lane == 0) TRACE(11, it);
     }
 
     // ---- epilogue: D^T[n, m] (lane = n, column = m) -> out[m, n] ------------------------------------------------------
@@ -399,7 +508,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   // ---- teardown ------------------------------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  if (prm.cluster > 1) {
+    cluster_sync_all();  // a peer may still be multicasting into / signalling this CTA
+  } else {
+    __syncthreads();
+  }
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -488,8 +601,19 @@ static int launch_cfg(const CUtensorMap& mx, const CUtensorMap& mw, const TcPara
     CB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(mx, mw, prm);
-  CB200_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = prm.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = prm.cluster > 1 ? 1 : 0;
+  CB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mx, mw, prm));
   return 0;
 }
 
@@ -524,13 +648,18 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
   const TcPlan pl = tc_plan(p.M, p.K, p.N);
   const int mt = pl.m_tile;
   const int pf = 32 / bits;
+  // CTAs with neighbouring n tiles and the same m tile share the x tile: each fetches 1/cluster of it and multicasts.
+  // (The kernel is bound by L2 -> SM traffic for x otherwise: every 128-column CTA re-reads the whole activation tile.)
+  const int n_tiles = (p.N + 127) / 128;
+  int cluster = g_tc_cluster > 0 ? g_tc_cluster : (mt >= 64 ? 4 : (mt >= 32 ? 2 : 1));
+  while (cluster > 1 && (n_tiles % cluster != 0 || mt / cluster < 8)) cluster /= 2;
 
   // x: [M, K] row-major -> dims {K, M}, box {64, m_tile}, 128-byte swizzle; rows beyond M are zero-filled by TMA
   CUtensorMap mx, mw;
   {
     const cuuint64_t dims[2] = {cuuint64_t(p.K), cuuint64_t(p.M)};
     const cuuint64_t strides[1] = {cuuint64_t(p.K) * 2};
-    const cuuint32_t box[2] = {64, cuuint32_t(mt)};
+    const cuuint32_t box[2] = {64, cuuint32_t(mt / cluster)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&mx, act_dtype == CB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                            const_cast<void*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -560,6 +689,10 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
   prm.kblocks_total = p.K / 64;
   prm.kb_per_split = pl.kb_per_split;
   prm.ws_partial = nullptr;
+  prm.cluster = cluster;
+#ifdef CB200_TC_TRACE
+  prm.trace = g_tc_trace;
+#endif
   if (pl.split_k > 1) {
     const size_t need = size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.split_k) * p.M * p.N * sizeof(float);
     if (!ws || ws_bytes < need) {

@@ -227,6 +227,22 @@ def test_tc_group_sizes_and_split_k(variant, g):
         lib.cb200_set_tc_tuning(0, 0)
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("variant", [_lib.TC_SS, _lib.TC_TS], ids=["ss", "ts"])
+def test_tc_cluster_multicast(cluster, variant):
+    """The activation tile is shared across a CTA cluster by TMA multicast: every cluster size gives the same bits."""
+    lib = _lib.load()
+    outs = []
+    try:
+        for cl in (1, cluster):
+            lib.cb200_set_tc_cluster(cl)
+            outs.append(_run_case(300, 2048, 1024, "uint4", 128, torch.float16, True, variant=variant))
+            _run_case(40, 1024, 512, "uint8b128", 128, torch.bfloat16, False, variant=variant)
+    finally:
+        lib.cb200_set_tc_cluster(0)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("variant", [_lib.TC_SS, _lib.TC_TS], ids=["ss", "ts"])
 def test_tc_one_hot_rows_reproduce_dequantised_weights(variant):
     """x = one-hot rows => out == W rows bit for bit: the tcgen05 path feeds the SAME dequant bits to the MMA."""
@@ -336,7 +352,8 @@ def test_full_size_row_selection_and_dequant(k, n):
 
 
 def test_batch_rows_equal_single_rows():
-    """Row m of an M=16 call equals the M=1 call on that row (same weights, same K order)."""
+    """Row m of an M=16 call equals the M=1 call on that row, within the budget between the two kernels the dispatcher
+    picks (M=16: tcgen05 kernel, W rounded to fp16 like the reference; M=1: fused decode kernel, W kept unrounded)."""
     from conch_b200 import quant_utils
 
     k, n = 4096, 6144
@@ -346,4 +363,4 @@ def test_batch_rows_equal_single_rows():
     full = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)
     for i in (0, 5, 15):
         one = mixed_precision_gemm(x[i : i + 1].contiguous(), wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)
-        torch.testing.assert_close(one[0], full[i], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(one[0], full[i], rtol=5e-3, atol=5e-3)
