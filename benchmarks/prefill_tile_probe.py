@@ -10,7 +10,7 @@ for name, m, k, n in (("8b_ffn", 4096, 4096, 14336), ("8b_ffn", 2048, 4096, 1433
     sets = [quant_utils.random_packed_weights(k, n, st, 128, torch.float16, "cuda", seed=i) for i in range(6)]
     x = torch.randn((m, k), device="cuda", dtype=torch.float16)
     out = torch.empty((m, n), device="cuda", dtype=torch.float16)
-    for mt, cl in ((256, 1), (256, 2), (256, 4), (128, 2), (128, 4)):
+    for mt, cl in ((256, 1), (256, 2), (128, 1)):
         lib.cb200_set_tc_tuning(mt, 1)
         lib.cb200_set_tc_cluster(cl)
         fns = [(lambda s=s: mixed_precision_gemm(x, s[0], s[1], s[2], 4, 0, 128, out=out, variant=_lib.TC_TS)) for s in sets]

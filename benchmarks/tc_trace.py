@@ -33,7 +33,7 @@ torch.cuda.synchronize()
 raw.cb200_debug_set_tc_trace(None)
 t = trace.cpu()
 t0 = int(t[t > 0].min())
-names = ["Wslot", "Xslot", "Mwait", "Mxfull", "Maready", "Missued", "Dtop", "Dmeta", "Dwfull", "Ddeq", "Dafree", "Dst"]
+names = ["Wslot", "Xslot", "Mwait", "Mxfull", "Maready", "Missued", "Dtop", "Dmeta", "Dwfull", "Ddeq", "Dafree", "Dst", "Mtrace2"]
 print("it   " + " ".join(f"{s:>8s}" for s in names))
 for it in range(k // 64):
-    print(f"{it:3d}  " + " ".join(f"{int(t[it, c]) - t0:8d}" if t[it, c] > 0 else "       -" for c in range(12)))
+    print(f"{it:3d}  " + " ".join(f"{int(t[it, c]) - t0:8d}" if t[it, c] > 0 else "       -" for c in range(13)))

@@ -6,11 +6,13 @@ Mirrors include/conch_b200.h one to one.  Loading fails loudly: there is no fall
 from __future__ import annotations
 
 import ctypes
+import os
 import pathlib
 import threading
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libconch_b200.so"
+# CB200_DEBUG_LIB=1 selects the instrumented build made with CB200_NVCC_EXTRA (benchmarks/tc_trace.py); still our CUDA library
+LIB_PATH = _PKG / ("libconch_b200_dbg.so" if os.environ.get("CB200_DEBUG_LIB") == "1" else "libconch_b200.so")
 
 # enums of include/conch_b200.h
 F16, BF16, F32 = 0, 1, 2

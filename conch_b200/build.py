@@ -17,8 +17,10 @@ import sys
 
 PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = PKG / "build"
-LIB = PKG / "libconch_b200.so"
+# CB200_NVCC_EXTRA (e.g. -DCB200_TC_TRACE for benchmarks/tc_trace.py) builds a separate debug library next to the product
+_DEBUG = bool(os.environ.get("CB200_NVCC_EXTRA", "").strip())
+OBJ = PKG / ("build_dbg" if _DEBUG else "build")
+LIB = PKG / ("libconch_b200_dbg.so" if _DEBUG else "libconch_b200.so")
 
 NVCC_FLAGS = [
     "-gencode",
@@ -31,7 +33,7 @@ NVCC_FLAGS = [
     "-fPIC",
     "-Xcompiler",
     "-fvisibility=hidden",
-    *os.environ.get("CB200_NVCC_EXTRA", "").split(),  # e.g. -DCB200_TC_TRACE for benchmarks/tc_trace.py (debug only)
+    *os.environ.get("CB200_NVCC_EXTRA", "").split(),
 ]
 
 

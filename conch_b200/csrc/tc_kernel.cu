@@ -324,37 +324,68 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #define TRACE(slot, it) do { } while (0)
 #endif
 
+  // The three single-thread roles below all follow one pattern: the WHOLE warp runs the loop convergently, lanes poll
+  // the barriers of several K blocks in ONE try_wait (different addresses per lane; a try_wait on an already completed
+  // barrier still costs ~140 cycles, so they must not be serialised), then one elected lane issues for all of them.
+  // (`elect.sync` instead of `lane == 0`: the compiler then emits straight-line UTMALDG / UTCHMMA code rather than a
+  // per-active-thread uniformisation loop around every such instruction.)
   if (warp == 0) {
     // ================================ TMA producer: packed weights ==================================================
-    if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % SW;
-        mbar_wait(w_free(s), ((it / SW) & 1) ^ 1);
-        TRACE(0, it);
-        mbar_expect_tx(w_full(s), Cfg::W_BYTES);
-        tma_load_2d(w_base + s * Cfg::W_BYTES, &tmap_w, n0, (kb0 + it) * Cfg::WROWS, w_full(s));
+    constexpr int UW = 4;
+    for (int it = 0; it < nk; it += UW) {
+      const int nb = min(UW, nk - it);
+      {
+        int i = it + (lane & (UW - 1));
+        if (i >= nk) i = it;
+        mbar_wait(w_free(i % SW), ((i / SW) & 1) ^ 1);
       }
+      __syncwarp();
+      TRACE(0, it);
+      if (elect_one()) {
+#pragma unroll
+        for (int u = 0; u < UW; ++u) {
+          if (u < nb) {
+            const int s = (it + u) % SW;
+            mbar_expect_tx(w_full(s), Cfg::W_BYTES);
+            tma_load_2d(w_base + s * Cfg::W_BYTES, &tmap_w, n0, (kb0 + it + u) * Cfg::WROWS, w_full(s));
+          }
+        }
+      }
+      __syncwarp();
     }
   } else if (warp == 3) {
     // ================================ TMA producer: activations =====================================================
-    if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % SX;
-        if (it >= SX) {  // slot last read by the MMAs of K block it - SX
-          const int j = it - SX;
+    constexpr int UX = 2;
+    for (int it = 0; it < nk; it += UX) {
+      const int nb = min(UX, nk - it);
+      {
+        int i = it + (lane & (UX - 1));
+        if (i >= nk) i = it;
+        if (i >= SX) {  // slot last read by the MMAs of K block i - SX
+          const int j = i - SX;
           mbar_wait(mma_done(j % SA), (j / SA) & 1);
         }
-        TRACE(1, it);
-        mbar_expect_tx(x_full(s), Cfg::X_BYTES);
-        if (prm.cluster > 1) {
-          // this CTA fetches rows [crank * MT/cluster, +MT/cluster) of the shared x tile and multicasts them to all
-          const uint32_t rows = MT / prm.cluster;
-          tma_load_2d_mc(x_base + s * Cfg::X_BYTES + crank * rows * 128, &tmap_x, (kb0 + it) * Cfg::KB, m0 + int(crank * rows),
-                         x_full(s), cmask);
-        } else {
-          tma_load_2d(x_base + s * Cfg::X_BYTES, &tmap_x, (kb0 + it) * Cfg::KB, m0, x_full(s));
+      }
+      __syncwarp();
+      TRACE(1, it);
+      if (elect_one()) {
+#pragma unroll
+        for (int u = 0; u < UX; ++u) {
+          if (u < nb) {
+            const int s = (it + u) % SX;
+            mbar_expect_tx(x_full(s), Cfg::X_BYTES);
+            if (prm.cluster > 1) {
+              // this CTA fetches rows [crank * MT/cluster, +MT/cluster) of the shared x tile and multicasts them to all
+              const uint32_t rows = MT / prm.cluster;
+              tma_load_2d_mc(x_base + s * Cfg::X_BYTES + crank * rows * 128, &tmap_x, (kb0 + it + u) * Cfg::KB,
+                             m0 + int(crank * rows), x_full(s), cmask);
+            } else {
+              tma_load_2d(x_base + s * Cfg::X_BYTES, &tmap_x, (kb0 + it + u) * Cfg::KB, m0, x_full(s));
+            }
+          }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================================================
@@ -365,36 +396,52 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // instruction descriptor: D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major (bits 15,16 = 0),
     // N>>3 at [17,23), M>>4 at [24,29)
     constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(MT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
-    for (int it = 0; it < nk; ++it) {
-      const int sx = it % SX, sa = it % SA;
+    // UM K blocks per round: lanes poll the 2 UM barriers {x_full, a_ready} x {it .. it + UM - 1} concurrently.
+    constexpr int UM = (TS && MT <= 128) ? 4 : 2;  // must stay <= SX and well below SA (the rings must keep slack)
+    static_assert(UM <= SX && UM < SA || !TS, "MMA round larger than the rings");
+    for (int it = 0; it < nk; it += UM) {
+      const int nb = min(UM, nk - it);
       TRACE(2, it);
-      mbar_wait(x_full(sx), (it / SX) & 1);
-      TRACE(3, it);
-      mbar_wait(a_ready(sa), (it / SA) & 1);
+      {
+        const int l = lane & (2 * UM - 1);
+        int i = it + (l >> 1);
+        if (i >= nk) i = it;
+        const uint32_t bar = (l & 1) ? a_ready(i % SA) : x_full(i % SX);
+        const uint32_t par = uint32_t((l & 1) ? (i / SA) : (i / SX)) & 1u;
+        mbar_wait(bar, par);
+      }
+      __syncwarp();
       TRACE(4, it);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t bdesc = make_sw128_desc(x_base + sx * Cfg::X_BYTES);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {  // four K=16 MMAs per 64-wide stage: +32 bytes inside the swizzle atom
-          const uint32_t acc = (it | k4) != 0;
-          if constexpr (TS) {
-            umma_ts(tmem_base, tmem_base + Cfg::A_COL0 + sa * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
-          } else {
-            const uint64_t adesc = make_sw128_desc(a_base + sa * Cfg::A_BYTES);
-            umma_ss(tmem_base, adesc + uint64_t(k4 * 2), bdesc + uint64_t(k4 * 2), idesc, acc);
+        for (int u = 0; u < UM; ++u) {
+          if (u < nb) {
+            const int sx = (it + u) % SX, sa = (it + u) % SA;
+            const uint64_t bdesc = make_sw128_desc(x_base + sx * Cfg::X_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {  // four K=16 MMAs per 64-wide K block: +32 bytes inside the swizzle atom
+              const uint32_t acc = (it | u | k4) != 0;
+              if constexpr (TS) {
+                umma_ts(tmem_base, tmem_base + Cfg::A_COL0 + sa * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
+              } else {
+                const uint64_t adesc = make_sw128_desc(a_base + sa * Cfg::A_BYTES);
+                umma_ss(tmem_base, adesc + uint64_t(k4 * 2), bdesc + uint64_t(k4 * 2), idesc, acc);
+              }
+            }
+            // once these MMAs have read them: release the A slot, and the x slot in every CTA that multicasts into it
+            if (prm.cluster > 1) {
+              umma_commit_mc(mma_done(sa), cmask);
+            } else {
+              umma_commit(mma_done(sa));
+            }
           }
         }
-        // once these MMAs have read them: release the A slot, and the x slot in every CTA that multicasts into it
-        if (prm.cluster > 1) {
-          umma_commit_mc(mma_done(sa), cmask);
-        } else {
-          umma_commit(mma_done(sa));
-        }
-        if (it == nk - 1) umma_commit(d_full);
+        if (it + nb == nk) umma_commit(d_full);
       }
       __syncwarp();
       TRACE(5, it);
+      TRACE(12, it);
     }
   } else if (warp >= 4) {
     // ================================ dequant warps, then epilogue ==================================================
@@ -405,33 +452,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const bool n_ok = n < p.N;
     const A* sp = reinterpret_cast<const A*>(p.s);
     A raw_s = A(0.f), raw_zf = A(0.f);
-    float raw_z = 0.f;
-    float zscalar = 0.f;
+    int raw_z = 0;  // integer zero-point kept RAW: converting at the load would stall on it one stage too early
+    int zscalar = 0;
     A zfscalar = A(0.f);
     if (ZK != CB200_ZP_NONE && p.zp_scalar) {
-      if constexpr (ZK == CB200_ZP_I32) zscalar = float(__ldg(reinterpret_cast<const int32_t*>(p.zp)));
-      if constexpr (ZK == CB200_ZP_U8) zscalar = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp)));
+      if constexpr (ZK == CB200_ZP_I32) zscalar = __ldg(reinterpret_cast<const int32_t*>(p.zp));
+      if constexpr (ZK == CB200_ZP_U8) zscalar = __ldg(reinterpret_cast<const uint8_t*>(p.zp));
       if constexpr (ZK == CB200_ZP_ACT) zfscalar = *reinterpret_cast<const A*>(p.zp);
     }
     const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
     // scale / zero-point of this thread's column for the group of K block `kb` (one prefetch ahead, raw)
+    // (group index kept incrementally: this set advances SETS K blocks per stage; no integer division in the loop)
+    const int gb = p.g / Cfg::KB;  // K blocks per quantisation group
+    int grp = (kb0 + set) / gb, grp_rem = (kb0 + set) % gb;
     auto fetch_meta = [&](int kb) {
       raw_z = zscalar;
       raw_zf = zfscalar;
-      if (!n_ok || kb >= kb1) return;
-      const size_t idx = size_t((kb * Cfg::KB) / p.g) * p.N + n;
-      raw_s = sp[idx];
-      if (zp_per_group) {
-        if constexpr (ZK == CB200_ZP_I32) raw_z = float(__ldg(reinterpret_cast<const int32_t*>(p.zp) + idx));
-        if constexpr (ZK == CB200_ZP_U8) raw_z = float(__ldg(reinterpret_cast<const uint8_t*>(p.zp) + idx));
-        if constexpr (ZK == CB200_ZP_ACT) raw_zf = reinterpret_cast<const A*>(p.zp)[idx];
+      if (n_ok && kb < kb1) {
+        const size_t idx = size_t(grp) * p.N + n;
+        raw_s = sp[idx];
+        if (zp_per_group) {
+          if constexpr (ZK == CB200_ZP_I32) raw_z = __ldg(reinterpret_cast<const int32_t*>(p.zp) + idx);
+          if constexpr (ZK == CB200_ZP_U8) raw_z = __ldg(reinterpret_cast<const uint8_t*>(p.zp) + idx);
+          if constexpr (ZK == CB200_ZP_ACT) raw_zf = reinterpret_cast<const A*>(p.zp)[idx];
+        }
+      }
+      grp_rem += SETS;
+      while (grp_rem >= gb) {
+        grp_rem -= gb;
+        ++grp;
       }
     };
     fetch_meta(kb0 + set);
 
     for (int it = set; it < nk; it += SETS) {
       const int sw = it % SW, sa = it % SA;
-      const ColQ cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, raw_z + float(p.bias), raw_zf);
+      const ColQ cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, float(raw_z + p.bias), raw_zf);
       if (q == 0 && lane == 0) TRACE(6, it);
       fetch_meta(kb0 + it + SETS);  // for this set's next stage; consumed one full stage later
       if (q == 0 && lane == 0) TRACE(7, it);
