@@ -6,13 +6,13 @@ from conch_b200.ops.quantization.gemm import mixed_precision_gemm
 
 lib = _lib.load()
 st = quant_utils.scalar_types.uint4
-for name, k, n in (("gate_up", 4096, 28672), ("down", 14336, 4096), ("o", 4096, 4096)):
+for name, k, n in (("qkv", 4096, 6144), ("gate_up", 4096, 28672), ("down", 14336, 4096), ("o", 4096, 4096)):
     wbytes = k * n // 2
     copies = copies_for_cold_l2(wbytes)
     sets = [quant_utils.random_packed_weights(k, n, st, 128, torch.float16, "cuda", seed=i) for i in range(copies)]
     x = torch.randn((1, k), device="cuda", dtype=torch.float16)
     out = torch.empty((1, n), device="cuda", dtype=torch.float16)
-    for mode in (1, 2):
+    for mode in (2,):
         for split in (0, 2, 4, 8, 16):
             for pdl in (0, 1):
                 lib.cb200_set_decode_tuning(mode, 0, split, 0)

@@ -17,15 +17,16 @@
 //     All cursors are linear pointer increments;
 //   * FUSED=false: nibbles are unpacked and W = (q - bias - zp) * s is formed per weight with dequant_word() -- the
 //     same bits as the dequant kernel and the reference's w_ref -- before the MMA;
-//   * FUSED=true: the magic-number operand itself, 0x6400|q = 1024 + q (fp16) or 0x4300|q = 128 + q (bf16), goes into
-//     the MMA, so a word costs 1 shift + 4 lop3 and NO floating-point op.  The offset is removed inside the tensor core
-//     too: a second MMA per operand pair multiplies the same activations with the per-column constant -(MAGIC + bias + zp)
-//     into the SAME accumulator, which therefore holds sum_k x_k (q_k - bias - zp) exactly (products of small integers
-//     and fp16/bf16 values are exact in fp32).  fp16 int4's odd nibbles arrive as 1024 + 16 q; their activations are
-//     pre-multiplied by 1/16 (exact except in the subnormal range, where the error cancels between the two MMAs).  The
-//     group scale is applied once per group to the fp32 sum: acc += s[n] * group_sum.  The result differs from the
-//     reference only by not rounding each W to fp16/bf16 -- far inside the 1e-2 tolerance; one-hot activations still
-//     reproduce the reference's W bit for bit;
+//   * FUSED=true: NO floating-point op per weight and no offset MMA.  fp16: the masked nibble / byte itself is the MMA
+//     operand -- the bit pattern 0x0000|v (v < 2048) read as fp16 is the subnormal (or first-binade) number v * 2^-24,
+//     exactly, and the tensor core multiplies subnormals exactly -- so a word costs 1 shift + 4 AND.  bf16 int4: the
+//     magic-number operand 0x4300|q = 128 + q (bf16 subnormals would push the fp32 products into the fp32 subnormal
+//     range).  The zero-point (and the 128) is removed per GROUP instead of per weight: one extra MMA per operand pair
+//     with an all-ones 16-row operand yields X[m] = sum_k x[m,k] of the group in the accumulator layout, and
+//         acc[m,n] += (s[n] * 2^24) * G[m,n] - (s[n] * zb[n]) * X[m]          (G = sum_k x q 2^-24, fp32, exact products)
+//     fp16 int4's nibbles at bits 4-7 arrive as 16 q; their activations are pre-multiplied by 1/16 (and the ones operand
+//     that meets them is 16.0).  The result differs from the reference only by not rounding each W to fp16/bf16 -- far
+//     inside the 1e-2 tolerance; one-hot activations still reproduce the reference's W bit for bit;
 //   * the dot product runs on the tensor pipe as mma.sync.m16n8k16 with the WEIGHTS as the 16-row operand (swap-AB) and
 //     x^T as the 8-column operand; the four lanes of a quad hold four different packed rows, so the K-reduction
 //     across lanes happens inside the MMA, fp32 accumulate; x is permuted in registers to the nibble order the cheap
@@ -33,15 +34,43 @@
 //   * S == 1: the warp stores its result directly.  S > 1: it writes an fp32 partial, bumps the column block's arrival
 //     counter, and the last arriver sums the S partials in slab order (deterministic, self-resetting counters: no
 //     memset, no second launch);
-//   * programmatic dependent launch (opt-in, cb200_set_pdl): the weight / metadata prefetch is issued BEFORE
-//     griddepcontrol.wait, so launch latency, prologue and the first DRAM round trip overlap the previous kernel's tail;
-//     x, the output and the workspace are only touched after the wait.
+//   * programmatic dependent launch (opt-in, cb200_set_pdl): a warp calls griddepcontrol.launch_dependents as soon as its
+//     own weight window is in flight, so the next kernel's CTAs become resident while this kernel's stragglers finish,
+//     issue THEIR weight / metadata prefetch (static data: legal before griddepcontrol.wait) and then block in
+//     griddepcontrol.wait; x, the output and the workspace are only touched after the wait.
+//   Measured anatomy of one launch (benchmarks/decode_trace.py, 58.7 MB layer): head 3.4 us (launch skew, 9.7 MB of
+//   first-window requests ramping the HBM up), main loop 12.0 us (5 TB/s), straggler tail + split-K arrival 3-4 us.  A
+//   stream-K variant (equal ranges of the linearised (column block, batch) space, every SM equally loaded) was built and
+//   measured: -8% on that layer, +8% on the smaller ones (second publish per straddling warp, longer prologue), no net
+//   gain on the bench -- not kept.
 #include "common.cuh"
 #include "dequant.cuh"
 
 namespace cb200 {
 
 DecodeTuning g_decode_tuning = {0, 0, 0, 0};
+
+#ifdef CB200_TC_TRACE  // debug builds only (benchmarks/decode_trace.py): globaltimer stamps of warp 0 of every CTA
+__device__ long long* g_dec_trace = nullptr;
+extern "C" __attribute__((visibility("default"))) void cb200_debug_set_decode_trace(void* p) {
+  cudaMemcpyToSymbol(g_dec_trace, &p, sizeof(p));
+}
+__device__ __forceinline__ void dec_stamp(int slot) {
+  if (g_dec_trace && (threadIdx.x & 127) == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_dec_trace[blockIdx.x * 8 + slot] = t;
+    if (slot == 0) {
+      unsigned sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      g_dec_trace[blockIdx.x * 8 + 7] = sm;
+    }
+  }
+}
+#define DEC_STAMP(slot) dec_stamp(slot)
+#else
+#define DEC_STAMP(slot) do { } while (0)
+#endif
 
 struct DecodeGeom {
   int m_rows;         // rows of x in this pass (<= 16)
@@ -104,6 +133,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
 
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  DEC_STAMP(0);
   if (w >= geo.total_warps) return;
   const int g8 = lane >> 2, tig = lane & 3;
   const int M = geo.m_rows;
@@ -117,17 +147,6 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   const int bpg = geo.bpg;
   const int col = cb * CW + VEC * g8; // first of this lane's four weight columns
   const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
-
-  // ---- weight window: WIN loads in flight before anything else (weights are static: legal before griddepcontrol.wait) ----
-  const char* wp = reinterpret_cast<const char*>(p.wq + (size_t(b0) * (U * 4) + tig) * N + col);
-  const size_t step_bytes = size_t(16) * N;  // 4 packed rows
-  uint4 win[WIN];
-#pragma unroll
-  for (int j = 0; j < WIN; ++j) {
-    win[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (j < nsteps) win[j] = ldg_stream_v4(wp + j * step_bytes);
-  }
-  wp += WIN * step_bytes;  // next load of slot j: wp + j * step_bytes
 
   // ---- per-warp shared memory: x slab [m_rows][x_row_bytes], group rows [ngroups][meta_row_bytes], one mbarrier -------------
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -145,6 +164,22 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
   }
   __syncwarp();
+  DEC_STAMP(1);
+  // ---- weight window: WIN loads in flight before anything else (weights are static: legal before griddepcontrol.wait) ----
+  const char* wp = reinterpret_cast<const char*>(p.wq + (size_t(b0) * (U * 4) + tig) * N + col);
+  const size_t step_bytes = size_t(16) * N;  // 4 packed rows
+  uint4 win[WIN];
+#pragma unroll
+  for (int j = 0; j < WIN; ++j) {
+    win[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (j < nsteps) win[j] = ldg_stream_v4(wp + j * step_bytes);
+  }
+  wp += WIN * step_bytes;  // next load of slot j: wp + j * step_bytes
+  // Programmatic dependent launch: release the NEXT kernel now.  Its CTAs become resident as ours retire, issue their
+  // own weight window and metadata copies, and then block in griddepcontrol.wait until this grid has completed -- so the
+  // next kernel's head (launch, prologue, first DRAM round trip) hides behind this kernel's tail.
+  if (geo.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   auto bulk = [&](uint32_t dst, const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
@@ -160,6 +195,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
     }
   }
 
+  DEC_STAMP(3);
   if (geo.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // x / out / workspace belong to the stream order
 
   // activations: row m of x, columns [b0 * U * STEP_K, + slab_k), one bulk copy per row
@@ -186,6 +222,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
     }
   }
 
+  DEC_STAMP(6);
   // ---- consume-side state ---------------------------------------------------------------------------------------------------
   float zscalar = 0.f;
   A zfscalar = A(0.f);
@@ -199,32 +236,39 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   const float fbias = float(p.bias);
   constexpr bool HALF = std::is_same<A, __half>::value;
   constexpr bool PRESCALE = FUSED && HALF && BITS == 4;  // odd nibbles are 1024 + 16 q: their activations get x 1/16
-  constexpr float MAGIC = HALF ? 1024.f : 128.f;
+  constexpr float MAGIC = HALF ? 0.f : 128.f;           // bf16 operands are 128 + q; fp16 operands are q * 2^-24
+  constexpr float OPSCALE = HALF ? 16777216.f : 1.f;    // 2^24 undoes the subnormal scaling
+  constexpr uint32_t ONE2 = HALF ? 0x3C003C00u : 0x3F803F80u;      // (1.0, 1.0)
+  constexpr uint32_t ONE2_ODD = PRESCALE ? 0x4C004C00u : ONE2;     // (16.0, 16.0) against activations scaled by 1/16
 
   ColQ cq[VEC];          // !FUSED: per-column dequant constants
-  float sc[VEC];         // FUSED: group scales as fp32
-  uint32_t offe[VEC];    // FUSED: pair (-(MAGIC + zb), same) per column           (plain operands)
-  uint32_t offo[VEC];    // FUSED: pair (-(MAGIC + 16 zb), same) per column        (x16 operands, fp16 int4 only)
+  float sa[VEC];         // FUSED: s[n] * 2^24 (fp16) | s[n] (bf16): multiplies G = sum_k x * operand
+  float sb[VEC];         // FUSED: -s[n] * zb (fp16) | -s[n] * (128 + zb) (bf16): multiplies X = sum_k x
 
   const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
   float acc[NT][MT][4];   // running (scaled) sum of this warp's slab
-  float accg[NT][MT][4];  // FUSED: exact sum_k x_k (q_k - zb) of the current group
+  float accg[NT][MT][4];  // FUSED: G of the current group (exact products, fp32 sum)
+  float accx[MT][4];      // FUSED: X[m] = sum_k x[m,k] of the current group, in the accumulator layout
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[t][mt][i] = accg[t][mt][i] = 0.f;
+      for (int i = 0; i < 4; ++i) acc[t][mt][i] = accg[t][mt][i] = accx[mt][i] = 0.f;
   bool group_open = false;  // FUSED: accg holds a partial group
 
-  auto close_group = [&]() {  // FUSED: acc += s[n] * group_sum
-    // C fragment: c0,c1 <- weight column 2t (m = 2tig, 2tig+1); c2,c3 <- weight column 2t+1 of this lane
+  auto close_group = [&]() {  // FUSED: acc += sa[n] * G[m,n] + sb[n] * X[m]
+    // C fragment: c0,c1 <- weight column 2t (m = 2tig, 2tig+1); c2,c3 <- weight column 2t+1 of this lane;
+    // the ones-MMA leaves X[2tig], X[2tig+1] in c0,c1 (and again in c2,c3)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int t = 0; t < NT; ++t)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[t][mt][i] = fmaf(sc[2 * t + (i >> 1)], accg[t][mt][i], acc[t][mt][i]);
+        for (int i = 0; i < 4; ++i) {
+          const float off = fmaf(sb[2 * t + (i >> 1)], accx[mt][i], acc[t][mt][i]);
+          acc[t][mt][i] = fmaf(sa[2 * t + (i >> 1)], accg[t][mt][i], off);
+        }
   };
 
   // ---- one batch: U steps out of window slots [W0, W0 + U); `step` is the index of its first step ------------------------------
@@ -256,10 +300,10 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         if constexpr (FUSED) {
-          sc[j] = ActOps<A>::to_float(s4[j]);
+          const float sj = ActOps<A>::to_float(s4[j]);
           const float zbj = (FZP ? ActOps<A>::to_float(zf[j]) : z[j]) + fbias;
-          offe[j] = ActOps<A>::pair(-(MAGIC + zbj), -(MAGIC + zbj));
-          offo[j] = PRESCALE ? ActOps<A>::pair(-(MAGIC + 16.f * zbj), -(MAGIC + 16.f * zbj)) : offe[j];
+          sa[j] = sj * OPSCALE;
+          sb[j] = -sj * (MAGIC + zbj);
         } else {
           cq[j] = make_colq<A, BITS, ORD, FZP>(s4[j], z[j] + fbias, zf[j]);
         }
@@ -293,21 +337,21 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
       uint32_t d[VEC][PAIRS];
       const bool fresh = !group_open && u == 0;  // first MMA of a group starts from zero instead of clearing registers
       if constexpr (FUSED) {
-        // magic-number operands, no arithmetic: fp16 0x6400|q (and 0x6400|(q<<4) for odd nibbles), bf16 0x4300|q
+        // operands without arithmetic: fp16 0x0000|v = v * 2^-24 (v = q, or 16 q for nibbles at bits 4-7), bf16 0x4300|q
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           if constexpr (BITS == 4 && HALF) {
             const uint32_t t8 = words[j] >> 8;
-            d[j][0] = lop3_and_or(words[j], 0x000f000fu, 0x64006400u);  // (1024+k0   , 1024+k4)
-            d[j][1] = lop3_and_or(words[j], 0x00f000f0u, 0x64006400u);  // (1024+16k1 , 1024+16k5)
-            d[j][2] = lop3_and_or(t8, 0x000f000fu, 0x64006400u);        // (k2, k6)
-            d[j][3] = lop3_and_or(t8, 0x00f000f0u, 0x64006400u);        // (16k3, 16k7)
+            d[j][0] = words[j] & 0x000f000fu;  // (k0   , k4)
+            d[j][1] = words[j] & 0x00f000f0u;  // (16 k1, 16 k5)
+            d[j][2] = t8 & 0x000f000fu;        // (k2, k6)
+            d[j][3] = t8 & 0x00f000f0u;        // (16 k3, 16 k7)
           } else if constexpr (BITS == 4) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) d[j][i] = lop3_and_or(words[j] >> (4 * i), 0x000f000fu, 0x43004300u);  // (128+k_i, 128+k_i+4)
           } else {
-            d[j][0] = prmt(words[j], 0x64646464u, 0x4140u);  // (1024+k0, 1024+k1)
-            d[j][1] = prmt(words[j], 0x64646464u, 0x4342u);  // (1024+k2, 1024+k3)
+            d[j][0] = prmt(words[j], 0u, 0x4140u);  // (k0, k1) * 2^-24
+            d[j][1] = prmt(words[j], 0u, 0x4342u);  // (k2, k3) * 2^-24
           }
         }
 #pragma unroll
@@ -328,9 +372,12 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
                 mma16816<A>(accg[t][mt], accg[t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
                             d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
               }
-              // offset: the same activations times -(MAGIC + zb) (resp. -(MAGIC + 16 zb)) into the same accumulator
-              mma16816<A>(accg[t][mt], accg[t][mt], offe[2 * t], offe[2 * t + 1], offo[2 * t], offo[2 * t + 1],
-                          xb[mt][2 * h], xb[mt][2 * h + 1]);
+            }
+            // X[m] += sum_k x[m,k] over this operand pair's 16 k (all 16 rows of the result are equal)
+            if (fresh && h == 0) {
+              mma16816<A>(accx[mt], zero4, ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
+            } else {
+              mma16816<A>(accx[mt], accx[mt], ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
             }
           }
         }
@@ -363,14 +410,14 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   // ---- main loop: two batches (the whole window) per iteration ------------------------------------------------------------------
   for (int i = 0; i < nunits; i += 2) {
     process(std::integral_constant<int, 0>{}, i * U);
+    if (i == 0) DEC_STAMP(4);
     if (i + 1 < nunits) process(std::integral_constant<int, U>{}, (i + 1) * U);
     wp += WIN * step_bytes;
   }
   if constexpr (FUSED) {
     if (group_open) close_group();  // slab ended inside a group (per-channel scales split across warps)
   }
-  // this warp has issued all of its loads: let the next kernel's CTAs start filling the slots our tail frees
-  if (geo.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  DEC_STAMP(5);
 
   // ---- publish -----------------------------------------------------------------------------------------------------------------
   if (S == 1) {  // this warp saw the whole K range: store directly
