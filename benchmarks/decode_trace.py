@@ -38,7 +38,7 @@ used = t[:, 0] > 0
 t = t[used]
 t0 = int(t[:, 0].min())
 print(f"{name}: {int(used.sum())} CTAs, event time {ev0.elapsed_time(ev1) * 1e3:.1f} us, SMs used {len(set(t[:, 7].tolist()))}")
-names = ["entry", "bar_init", "win_issued", "meta_issued", "batch0", "loop_end", "staged"]
+names = ["entry", "win_issued", "meta_issued", "pdl_wait", "batch0", "loop_end", "staged"]
 for c, nm in enumerate(names):
     v = (t[:, c][t[:, c] > 0] - t0).float()
     if len(v) == 0:

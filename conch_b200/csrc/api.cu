@@ -39,7 +39,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 static int validate(const void* x, const void* wq, const void* ws, const void* wzp, const void* out, int64_t M,
                     int64_t K, int64_t N, int bits, int64_t* group_size, int act_dtype, int out_dtype, int zp_kind,
-                    bool need_x) {
+                    bool zp_scalar, bool need_x) {
   if ((need_x && !x) || !wq || !ws || !out) {
     set_error("null pointer argument");
     return CB200_ERR_ARG;
@@ -80,8 +80,10 @@ static int validate(const void* x, const void* wq, const void* ws, const void* w
     set_error("dimension too large");
     return CB200_ERR_SHAPE;
   }
-  if ((need_x && !aligned16(x)) || !aligned16(wq) || !aligned16(out) || (reinterpret_cast<uintptr_t>(ws) & 7u)) {
-    set_error("x, w_q_packed and out must be 16-byte aligned, w_s 8-byte aligned");
+  // (per-group zero-points are read with 16-byte loads like the scales; a scalar zero-point may sit anywhere)
+  if ((need_x && !aligned16(x)) || !aligned16(wq) || !aligned16(out) || !aligned16(ws) ||
+      (wzp && zp_kind != CB200_ZP_NONE && !zp_scalar && !aligned16(wzp))) {
+    set_error("x, w_q_packed, w_s, per-group w_zp and out must be 16-byte aligned");
     return CB200_ERR_ARG;
   }
   return 0;
@@ -119,7 +121,7 @@ int cb200_dequantize(const void* w_q_packed, const void* w_s, const void* w_zp, 
   int rc = check_device();
   if (rc) return rc;
   rc = validate(nullptr, w_q_packed, w_s, w_zp, w_out, 1, K, N, weight_size_bits, &group_size, act_dtype, act_dtype,
-                zp_kind, false);
+                zp_kind, zp_is_scalar != 0, false);
   if (rc) return rc;
   Problem p{};
   p.wq = reinterpret_cast<const uint32_t*>(w_q_packed);
@@ -146,7 +148,7 @@ int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const v
   int rc = check_device();
   if (rc) return rc;
   rc = validate(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, &group_size, act_dtype, out_dtype, zp_kind,
-                true);
+                zp_is_scalar != 0, true);
   if (rc) return rc;
   if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 15u)) {
     set_error("workspace must be 16-byte aligned");

@@ -40,7 +40,10 @@
 //     griddepcontrol.wait; x, the output and the workspace are only touched after the wait.
 //   Measured anatomy of one launch (benchmarks/decode_trace.py, 58.7 MB layer): head 3.4 us (launch skew, 9.7 MB of
 //   first-window requests ramping the HBM up), main loop 12.0 us (5 TB/s), straggler tail + split-K arrival 3-4 us.  A
-//   stream-K variant (equal ranges of the linearised (column block, batch) space, every SM equally loaded) was built and
+//   Plain 16-byte loads for the scale / zero-point rows were measured too: behind the weight window they block at issue
+//   until the window drains (+2.9 us), in front of it they push the window out of the load queue (~100 512-byte requests
+//   per SM is all the LSU tracks) -- hence the TMA bulk copies, which bypass that queue, at ~40 ns of issue time each.
+//   A stream-K variant (equal ranges of the linearised (column block, batch) space, every SM equally loaded) was built and
 //   measured: -8% on that layer, +8% on the smaller ones (second publish per straddling warp, longer prologue), no net
 //   gain on the bench -- not kept.
 #include "common.cuh"
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   // own weight window and metadata copies, and then block in griddepcontrol.wait until this grid has completed -- so the
   // next kernel's head (launch, prologue, first DRAM round trip) hides behind this kernel's tail.
   if (geo.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  DEC_STAMP(2);
 
   auto bulk = [&](uint32_t dst, const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
