@@ -58,6 +58,15 @@ _DTYPE_CODE = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32
 
 # (device index, stream handle) -> uint8 workspace tensor whose counter prefix is zero between launches
 _workspaces: dict[tuple[int, int], torch.Tensor] = {}
+_need_cache: dict[tuple[int, int, int, int, int], int] = {}
+
+
+def _raw_stream(index: int) -> int:
+    """cudaStream_t of torch's current stream on device `index` (the private fast accessor when it exists)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(index)
+    except AttributeError:  # pragma: no cover - older / newer torch without the private hook
+        return torch.cuda.current_stream(index).cuda_stream
 
 
 def _workspace(device: torch.device, stream: int, nbytes: int) -> torch.Tensor:
@@ -99,9 +108,15 @@ def mixed_precision_gemm_launcher(
     """
     lib = _lib.load()
     device = x.device
-    stream = torch.cuda.current_stream(device).cuda_stream
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    stream = _raw_stream(index)
     m, k, n = metadata.m_dim, metadata.k_dim, metadata.n_dim
-    need = lib.cb200_mpgemm_workspace_bytes(m, k, n, metadata.weight_size_bits, variant)
+    # the scratch size of a shape is cached (one ctypes call less per launch); the tuning knobs can change it, in which
+    # case the library answers CB200_ERR_WORKSPACE and the size is queried again below
+    key = (m, k, n, metadata.weight_size_bits, variant)
+    need = _need_cache.get(key)
+    if need is None:
+        need = _need_cache[key] = lib.cb200_mpgemm_workspace_bytes(m, k, n, metadata.weight_size_bits, variant)
     ws = _workspace(device, stream, need)
     zp_kind = zero_point_kind(x, w_zp)
     args = (
@@ -123,11 +138,17 @@ def mixed_precision_gemm_launcher(
         variant,
         stream,
     )  # fmt: skip
-    if device.index is not None and device.index != torch.cuda.current_device():
+    if index != torch.cuda.current_device():
         with torch.cuda.device(device):
             rc = lib.cb200_mpgemm(*args)
     else:
         rc = lib.cb200_mpgemm(*args)
+    if rc == _lib.ERR_WORKSPACE:  # stale cached size (a tuning knob changed the plan): ask again, grow, retry once
+        need = _need_cache[key] = lib.cb200_mpgemm_workspace_bytes(m, k, n, metadata.weight_size_bits, variant)
+        ws = _workspace(device, stream, need)
+        args = args[:15] + (ws.data_ptr(), ws.numel()) + args[17:]
+        with torch.cuda.device(device):
+            rc = lib.cb200_mpgemm(*args)
     _lib.raise_for_status(rc)
 
 
