@@ -383,7 +383,7 @@ def run_gpu_arm(args) -> None:
                 "frac": per_gpu / peak,
                 "traffic": traffic,
                 "peak_source": peak_src,
-                "kernel": "cb200::decode_kernel<__half,4,1,4,CB200_ZP_I32,false>",
+                "kernel": "cb200::decode_kernel<__half,4,1,4,CB200_ZP_I32,FUSED=true>",
                 "algorithmic_bytes_per_launch": algorithmic_bytes() / (LAYERS * len(PROJECTIONS)),
                 "avg_launch_us": ms_per_step * 1e3 / (LAYERS * len(PROJECTIONS)),
             },
@@ -399,6 +399,8 @@ def run_gpu_arm(args) -> None:
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(),
         }
+        if world == 1:
+            line["prefill"] = prefill_probe(dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
             res = cpu_reference(steps=5, warmup=1)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
@@ -410,6 +412,50 @@ def run_gpu_arm(args) -> None:
         dist.barrier()
         torch.cuda.synchronize()
         os._exit(0)
+
+
+def prefill_probe(dev, peaks: dict) -> dict:
+    """Second regime of the same op, reported next to the decode headline: M=4096 x (K=4096, N=14336) W4A16 through the
+    tcgen05 kernel, CUDA-event timed over weight copies that rotate (6 x 29 MB of packed weights + 33 MB of x per call)."""
+    import torch
+
+    from conch_b200 import _lib, quant_utils
+    from conch_b200.ops.quantization.gemm import mixed_precision_gemm
+
+    m, k, n = 4096, 4096, 14336
+    st = quant_utils.scalar_types.uint4
+    sets = [quant_utils.random_packed_weights(k, n, st, GROUP, torch.float16, dev, seed=100 + i) for i in range(6)]
+    x = torch.randn((m, k), device=dev, dtype=torch.float16)
+    out = torch.empty((m, n), device=dev, dtype=torch.float16)
+    for s_ in sets:
+        mixed_precision_gemm(x, s_[0], s_[1], s_[2], BITS, BIAS, GROUP, out=out)
+    torch.cuda.synchronize(dev)
+    iters = 24
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(iters):
+        s_ = sets[i % len(sets)]
+        mixed_precision_gemm(x, s_[0], s_[1], s_[2], BITS, BIAS, GROUP, out=out)
+    stop.record()
+    stop.synchronize()
+    us = start.elapsed_time(stop) * 1e3 / iters
+    tflops = 2.0 * m * n * k / us / 1e6
+    peak = float(peaks.get("bf16_tflops", 2250.0))
+    return {
+        "workload": "llama3-8b-w4a16-prefill M=4096 K=4096 N=14336 (uint4+zp_int32, g128, fp16)",
+        "kernel": "cb200::tc_kernel (" + _lib.VARIANT_NAMES[_lib.load().cb200_last_variant()] + ")",
+        "us": us,
+        "tflops": tflops,
+        "roofline": {
+            "bound": "tensor",
+            "achieved": tflops,
+            "peak": peak,
+            "unit": "TFLOP/s",
+            "frac": tflops / peak,
+            "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if "bf16_tflops" in peaks else "nominal dense fp16",
+            "frac_of_sustained": tflops / float(peaks["bf16_tflops_sustained"]) if "bf16_tflops_sustained" in peaks else None,
+        },
+    }
 
 
 def main() -> None:
