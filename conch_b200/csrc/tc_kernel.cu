@@ -32,7 +32,7 @@
 namespace cb200 {
 
 TcTuning g_tc_tuning = {0, 0};
-int g_tc_cluster = 0;  // 0 = heuristic
+int g_tc_cluster = 0;  // 0 = default (no cluster)
 #ifdef CB200_TC_TRACE
 long long* g_tc_trace = nullptr;
 extern "C" __attribute__((visibility("default"))) void cb200_debug_set_tc_trace(void* p) { g_tc_trace = reinterpret_cast<long long*>(p); }
@@ -704,10 +704,11 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
   const TcPlan pl = tc_plan(p.M, p.K, p.N);
   const int mt = pl.m_tile;
   const int pf = 32 / bits;
-  // CTAs with neighbouring n tiles and the same m tile share the x tile: each fetches 1/cluster of it and multicasts.
-  // (The kernel is bound by L2 -> SM traffic for x otherwise: every 128-column CTA re-reads the whole activation tile.)
+  // Optional (cb200_set_tc_cluster): CTAs with neighbouring n tiles and the same m tile share the x tile -- each fetches
+  // 1/cluster of it and multicasts.  Measured neutral (2) to slightly slower (4) on every prefill shape: the x traffic
+  // from L2 is not what limits this kernel, so the default is no cluster.
   const int n_tiles = (p.N + 127) / 128;
-  int cluster = g_tc_cluster > 0 ? g_tc_cluster : (mt >= 64 ? 4 : (mt >= 32 ? 2 : 1));
+  int cluster = g_tc_cluster > 0 ? g_tc_cluster : 1;
   while (cluster > 1 && (n_tiles % cluster != 0 || mt / cluster < 8)) cluster /= 2;
 
   // x: [M, K] row-major -> dims {K, M}, box {64, m_tile}, 128-byte swizzle; rows beyond M are zero-filled by TMA

@@ -107,7 +107,8 @@ CB200_API int cb200_dequantize(const void* w_q_packed, const void* w_s, const vo
 CB200_API void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_words);
 /* Debug/tuning knobs for the tcgen05 family: m_tile (MMA N: 16..256, 0 = heuristic), split_k (0 = heuristic). */
 CB200_API void cb200_set_tc_tuning(int m_tile, int split_k);
-/* CTAs per cluster sharing one activation tile through TMA multicast in the tcgen05 family (1, 2, 4; 0 = heuristic). */
+/* CTAs per cluster sharing one activation tile through TMA multicast in the tcgen05 family (1, 2, 4; 0 = default = 1:
+ * measured neutral). */
 CB200_API void cb200_set_tc_cluster(int ctas);
 
 /* Programmatic dependent launch for the decode kernels (default off).  When enabled, a decode kernel may start while the
