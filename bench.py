@@ -249,15 +249,27 @@ def run_gpu_arm(args) -> None:
 
     def step(count: bool = False):
         nonlocal launches_per_step
+        pending = None  # the previous GEMM's all-gather: enqueued on NCCL's stream, waited for one launch later
         for layer in range(LAYERS):
             for pi in range(len(PROJECTIONS)):
                 packed, w_s, w_zp = weights[layer][pi]
-                if world > 1:
-                    sharded[layer][pi].gathered(xs[pi], out=outs[layer][pi])  # GEMM on the shard + NCCL all-gather
+                if world > 1 and args.nccl_gather:
+                    # GEMM on the shard + NCCL all-gather of its output; the transfer overlaps the next GEMM
+                    _, work = sharded[layer][pi].gathered_async(xs[pi], out=outs[layer][pi])
+                    if pending is not None:
+                        pending.wait()
+                    pending = work
+                elif world > 1:
+                    # fused gather: the GEMV kernel's epilogue stores its slice into every rank's gather buffer (P2P)
+                    sharded[layer][pi].pushed(xs[pi])
                 else:
                     mixed_precision_gemm(xs[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=outs[layer][pi])
                 if count:
                     launches_per_step += lib.cb200_last_launch_count()
+        if pending is not None:
+            pending.wait()
+        if world > 1 and not args.nccl_gather:
+            sharded[0][0].sync()  # ONE cross-GPU barrier per token: every rank now holds all 128 gathered outputs
 
     def barrier():
         if world > 1:
@@ -320,13 +332,26 @@ def run_gpu_arm(args) -> None:
     def e2e_step():
         for pi in range(len(PROJECTIONS)):
             x_dev[pi].copy_(x_host[pi], non_blocking=True)
+        pending = None
         for layer in range(LAYERS):
             for pi in range(len(PROJECTIONS)):
                 packed, w_s, w_zp = weights[layer][pi]
-                if world > 1:
-                    sharded[layer][pi].gathered(x_dev[pi], out=out_views[layer][pi].view(M, -1))
+                if world > 1 and args.nccl_gather:
+                    _, work = sharded[layer][pi].gathered_async(x_dev[pi], out=out_views[layer][pi].view(M, -1))
+                    if pending is not None:
+                        pending.wait()
+                    pending = work
+                elif world > 1:
+                    sharded[layer][pi].pushed(x_dev[pi])
                 else:
                     mixed_precision_gemm(x_dev[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=out_views[layer][pi].view(M, -1))
+        if pending is not None:
+            pending.wait()
+        if world > 1 and not args.nccl_gather:
+            sharded[0][0].sync()
+            # this rank's own slices (the result it computed) go back to the host, like the single-GPU arm
+            torch.cat([sharded[layer][pi].pushed_local_view(M) for layer in range(LAYERS) for pi in range(len(PROJECTIONS))],
+                      dim=1, out=out_dev.view(1, -1))
         out_host.copy_(out_dev, non_blocking=True)
 
     e2e_steps = max(3, min(args.steps, 50))
@@ -372,7 +397,7 @@ def run_gpu_arm(args) -> None:
                 "launch": ("cuda-graph replay of the 128 GEMV launches" if graph is not None else "eager python launches")
                 + ("" if args.no_pdl else ", programmatic dependent launch"),
                 "l2": "inputs larger than L2: 3.49 GB of packed weights per step vs 126 MB L2",
-                "sharding": "none" if world == 1 else f"N-sharded x{world}, NCCL all_gather_into_tensor after every GEMM",
+                "sharding": "none" if world == 1 else (f"N-sharded x{world}, NCCL all_gather_into_tensor after every GEMM (async: the gather of GEMM i overlaps GEMM i+1)" if args.nccl_gather else f"N-sharded x{world}, fused gather: every GEMV kernel stores its slice into all {world} ranks' gather buffers (P2P over NVLink, cb200_mpgemm_push), one cross-GPU barrier per token"),
             },
             "tflops": flops() * world / (ms_per_step * 1e-3) / 1e12,
             "roofline": {
@@ -464,6 +489,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: NCCL all-gather after every GEMM instead of the fused P2P push")
     ap.add_argument("--no-graph", action="store_true", help="time eager Python launches instead of a CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between the GEMVs")

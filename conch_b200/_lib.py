@@ -28,6 +28,7 @@ EXPORTS = (
     "cb200_last_error",
     "cb200_mpgemm_workspace_bytes",
     "cb200_mpgemm",
+    "cb200_mpgemm_push",
     "cb200_last_variant",
     "cb200_last_launch_count",
     "cb200_dequantize",
@@ -79,6 +80,8 @@ def load() -> ctypes.CDLL:
             c_void_p, c_size_t,  # workspace
             c_int, c_void_p,  # variant, stream
         ]  # fmt: skip
+        lib.cb200_mpgemm_push.restype = c_int
+        lib.cb200_mpgemm_push.argtypes = lib.cb200_mpgemm.argtypes + [ctypes.POINTER(c_void_p), c_int]  # peer_out, num_peers
         lib.cb200_dequantize.restype = c_int
         lib.cb200_dequantize.argtypes = [
             c_void_p, c_void_p, c_void_p, c_void_p,

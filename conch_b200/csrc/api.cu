@@ -143,6 +143,14 @@ int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const v
                  int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
                  int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
                  void* stream) {
+  return cb200_mpgemm_push(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, weight_bias, group_size, act_dtype,
+                           out_dtype, zp_kind, zp_is_scalar, workspace, workspace_bytes, variant, stream, nullptr, 0);
+}
+
+int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M,
+                      int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
+                      int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
+                      void* stream, void* const* peer_out, int num_peers) {
   tls_last_variant = 0;
   tls_last_launches = 0;
   int rc = check_device();
@@ -168,6 +176,18 @@ int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const v
   p.zp_kind = zp_kind;
   p.zp_scalar = zp_is_scalar;
   p.out_dtype = out_dtype;
+  if (num_peers < 0 || num_peers > CB200_MAX_PEERS || (num_peers > 0 && !peer_out)) {
+    set_error("num_peers=%d out of range (0..%d)", num_peers, CB200_MAX_PEERS);
+    return CB200_ERR_ARG;
+  }
+  p.n_peers = num_peers;
+  for (int i = 0; i < num_peers; ++i) {
+    if (!peer_out[i] || !aligned16(peer_out[i])) {
+      set_error("peer_out[%d] is null or not 16-byte aligned", i);
+      return CB200_ERR_ARG;
+    }
+    p.peer_out[i] = peer_out[i];
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   int chosen = variant;
@@ -177,6 +197,11 @@ int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const v
     // pipeline (measured, profiles/r01_midm_probe.log)
     const bool decode = M <= 8 || (M <= 16 && K * N > (int64_t(32) << 20));
     chosen = (decode || !tc_supported(p, weight_size_bits)) ? CB200_DECODE_MMA : CB200_TC_TS;
+  }
+  if (num_peers > 0 && chosen != CB200_DECODE_MMA) {
+    // the fused push lives in the decode kernel's (tiny) epilogue; big outputs are bandwidth-bound: all-gather them
+    set_error("cb200_mpgemm_push: only the decode kernel (M <= 16) stores to peers; use an all-gather for M=%lld", (long long)M);
+    return CB200_ERR_UNSUPPORTED;
   }
   int launches = 0;
   if (chosen == CB200_DECODE_MMA) {

@@ -13,6 +13,8 @@
 namespace cb200 {
 
 // One mixed-precision GEMM problem, as the kernels see it (all device pointers).
+constexpr int CB200_MAX_PEERS = 7;  // 8 GPUs per node
+
 struct Problem {
   const void* x;       // [M, K] act
   const uint32_t* wq;  // [K/pf, N] packed
@@ -25,6 +27,8 @@ struct Problem {
   int zp_kind;      // cb200_zp_kind
   int zp_scalar;    // w_zp.numel() == 1
   int out_dtype;    // cb200_dtype
+  int n_peers;      // cb200_mpgemm_push: the result is also stored into peer_out[0 .. n_peers) (same [M, N] layout)
+  void* peer_out[CB200_MAX_PEERS];
 };
 
 void set_error(const char* fmt, ...);
@@ -69,6 +73,13 @@ __device__ __forceinline__ void store_out(void* out, int out_dtype, size_t idx, 
   } else {
     reinterpret_cast<float*>(out)[idx] = v;
   }
+}
+
+// out[idx] = v, and the same element of every peer buffer (multi-GPU epilogue: P2P stores over NVLink)
+template <class T>
+__device__ __forceinline__ void store_out_all(const Problem& p, size_t idx, float v) {
+  store_out<T>(p.out, p.out_dtype, idx, v);
+  for (int i = 0; i < p.n_peers; ++i) store_out<T>(p.peer_out[i], p.out_dtype, idx, v);
 }
 
 // streaming (read-once) global loads: bypass L1 allocation

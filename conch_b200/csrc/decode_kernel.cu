@@ -433,12 +433,12 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         const int m = mt * 8 + 2 * tig;
         const int n = col + 2 * t;
         if (m < M) {
-          store_out<A>(p.out, p.out_dtype, size_t(m) * N + n, acc[t][mt][0]);
-          store_out<A>(p.out, p.out_dtype, size_t(m) * N + n + 1, acc[t][mt][2]);
+          store_out_all<A>(p, size_t(m) * N + n, acc[t][mt][0]);
+          store_out_all<A>(p, size_t(m) * N + n + 1, acc[t][mt][2]);
         }
         if (m + 1 < M) {
-          store_out<A>(p.out, p.out_dtype, size_t(m + 1) * N + n, acc[t][mt][1]);
-          store_out<A>(p.out, p.out_dtype, size_t(m + 1) * N + n + 1, acc[t][mt][3]);
+          store_out_all<A>(p, size_t(m + 1) * N + n, acc[t][mt][1]);
+          store_out_all<A>(p, size_t(m + 1) * N + n + 1, acc[t][mt][3]);
         }
       }
     return;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
     float v = 0.f;
     for (int s = 0; s < S; ++s) v += __ldcg(base + size_t(s) * (M * CW) + e);
     const int m = e / CW, lc = e - m * CW;
-    store_out<A>(p.out, p.out_dtype, size_t(m) * N + cb * CW + lc, v);
+    store_out_all<A>(p, size_t(m) * N + cb * CW + lc, v);
   }
   if (lane == 0) ws_counter[cb] = 0u;  // leave the counter clean for the next launch
 }

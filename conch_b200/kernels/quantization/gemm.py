@@ -8,6 +8,8 @@ it does not allocate the output; the only memory it owns is a cached split-K wor
 
 from __future__ import annotations
 
+import ctypes
+from collections.abc import Sequence
 from dataclasses import dataclass
 from enum import Enum
 
@@ -101,10 +103,13 @@ def mixed_precision_gemm_launcher(
     metadata: MixedPrecisionMatmulMetadata,
     *,
     variant: int = _lib.AUTO,
+    peer_out_ptrs: Sequence[int] | None = None,
 ) -> None:
     """Enqueue out = x @ dequant(W) on the current CUDA stream.  Never synchronises.
 
     Counterpart of the reference launcher (conch/kernels/quantization/gemm.py:482-545): same argument order.
+    `peer_out_ptrs` (multi-GPU, decode regime): device pointers of other GPUs' [M, N] buffers the kernel's epilogue also
+    stores the result to (`cb200_mpgemm_push`, see conch_b200/sharded.py).
     """
     lib = _lib.load()
     device = x.device
@@ -138,17 +143,21 @@ def mixed_precision_gemm_launcher(
         variant,
         stream,
     )  # fmt: skip
+    entry = lib.cb200_mpgemm
+    if peer_out_ptrs:
+        entry = lib.cb200_mpgemm_push
+        args = args + ((ctypes.c_void_p * len(peer_out_ptrs))(*peer_out_ptrs), len(peer_out_ptrs))
     if index != torch.cuda.current_device():
         with torch.cuda.device(device):
-            rc = lib.cb200_mpgemm(*args)
+            rc = entry(*args)
     else:
-        rc = lib.cb200_mpgemm(*args)
+        rc = entry(*args)
     if rc == _lib.ERR_WORKSPACE:  # stale cached size (a tuning knob changed the plan): ask again, grow, retry once
         need = _need_cache[key] = lib.cb200_mpgemm_workspace_bytes(m, k, n, metadata.weight_size_bits, variant)
         ws = _workspace(device, stream, need)
         args = args[:15] + (ws.data_ptr(), ws.numel()) + args[17:]
         with torch.cuda.device(device):
-            rc = lib.cb200_mpgemm(*args)
+            rc = entry(*args)
     _lib.raise_for_status(rc)
 
 

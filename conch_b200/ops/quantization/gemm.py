@@ -12,6 +12,7 @@ There is no CPU / Triton fallback: inputs must live on a B200.
 
 from __future__ import annotations
 
+from collections.abc import Sequence
 from typing import Final
 
 import torch
@@ -178,11 +179,13 @@ def mixed_precision_gemm(
     strict: bool = False,
     variant: int = _lib.AUTO,
     out: torch.Tensor | None = None,
+    peer_out_ptrs: Sequence[int] | None = None,
 ) -> torch.Tensor:
     """Mixed precision GEMM: `x[M,K] @ dequant(w_q_packed[K/pf,N], w_s, w_zp) -> [M,N]`.
 
-    Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus two optional keywords:
-    `variant` forces a kernel family (debug / benchmarking), `out` reuses a caller-owned output buffer.
+    Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus three optional keywords:
+    `variant` forces a kernel family (debug / benchmarking), `out` reuses a caller-owned output buffer, `peer_out_ptrs`
+    (multi-GPU, M <= 16) lists peer-GPU buffers the kernel also stores the result to (conch_b200/sharded.py).
     """
     _require_device(x, w_q_packed, w_s, w_zp)
     metadata = create_mixed_precision_metadata(
@@ -200,7 +203,7 @@ def mixed_precision_gemm(
         raise ValueError("`out` must be a contiguous [M, N] tensor of the output dtype")
     if metadata.m_dim == 0:
         return out
-    mixed_precision_gemm_launcher(out, x, w_q_packed, w_s, w_zp, metadata, variant=variant)
+    mixed_precision_gemm_launcher(out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs)
     return out
 
 

@@ -64,6 +64,7 @@ class ShardedMixedPrecisionLinear:
         self._gemm = gemm_fn
         self._gather_buf: torch.Tensor | None = None
         self._local_buf: torch.Tensor | None = None
+        self._symm: dict[tuple[int, torch.dtype], tuple[torch.Tensor, object, list[int]]] = {}
 
     def local(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         """This rank's `[M, N/G]` slice of the output (no communication)."""
@@ -71,15 +72,73 @@ class ShardedMixedPrecisionLinear:
 
     def gathered(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         """`[G, M, N/G]`: shard-major layout straight out of the all-gather (no extra copy)."""
+        out, work = self.gathered_async(x, **kwargs)
+        if work is not None:
+            work.wait()
+        return out
+
+    def gathered_async(self, x: torch.Tensor, **kwargs) -> tuple[torch.Tensor, "dist.Work | None"]:
+        """Like `gathered`, but the all-gather is only ENQUEUED (on the process group's own stream): returns the
+        `[G, M, N/G]` view and the pending work.  The caller may launch independent work -- e.g. the next layer's GEMM --
+        before `work.wait()`, so the NVLink transfer overlaps it; the view is valid after the wait."""
         y = self.local(x, **kwargs)
         if self.world == 1:
-            return y.unsqueeze(0)
+            return y.unsqueeze(0), None
         m = y.shape[0]
         if self._gather_buf is None or self._gather_buf.shape[0] != self.world * m or self._gather_buf.dtype != y.dtype:
             # concatenation along dim 0 (what both NCCL and gloo expect), viewed as [G, M, N/G] below
             self._gather_buf = torch.empty((self.world * m, self.n_local), device=y.device, dtype=y.dtype)
-        dist.all_gather_into_tensor(self._gather_buf, y.contiguous(), group=self.group)
-        return self._gather_buf.view(self.world, m, self.n_local)
+        work = dist.all_gather_into_tensor(self._gather_buf, y.contiguous(), group=self.group, async_op=True)
+        return self._gather_buf.view(self.world, m, self.n_local), work
+
+    # ---- fused gather: the GEMM kernel's own epilogue stores into every rank's gather buffer (P2P over NVLink) ----------
+    PUSH_MAX_ROWS = 8  # the decode kernel is what AUTO picks up to here for every shape (cb200_mpgemm_push is decode-only)
+
+    def _symmetric(self, m: int, dtype: torch.dtype, device: torch.device):
+        """`[G, M, N/G]` gather buffer in symmetric memory (every rank maps every rank's copy), allocated once per (M, dtype).
+        COLLECTIVE on first use: all ranks must call with the same M and dtype."""
+        key = (m, dtype)
+        if key not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty((self.world, m, self.n_local), dtype=dtype, device=device)
+            group = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, group.group_name)
+            slot = self.rank * m * self.n_local * buf.element_size()  # this rank's slot inside EVERY rank's buffer
+            peers = [int(hdl.buffer_ptrs[p]) + slot for p in range(self.world) if p != self.rank]
+            self._symm[key] = (buf, hdl, peers)
+        return self._symm[key]
+
+    def pushed(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
+        """GEMM on the shard whose epilogue stores the `[M, N/G]` result into slot `rank` of EVERY rank's gather buffer
+        (`cb200_mpgemm_push`: plain P2P stores over NVLink / NVSwitch from the decode kernel -- no all-gather kernel, no
+        NCCL latency).  Returns this rank's `[G, M, N/G]` buffer; the peers' slots are complete after `sync()`, one
+        cross-GPU barrier that can cover any number of pushed layers (e.g. once per token).  Re-using the buffer for the
+        next token while a peer may still read it needs a second `sync()` -- the caller's protocol.  M <= 8 only
+        (decode regime); larger M should use `gathered()` (bandwidth-bound: NCCL is the right tool)."""
+        m = x.shape[0]
+        if self.world == 1:
+            return self.local(x, **kwargs).unsqueeze(0)
+        if m > self.PUSH_MAX_ROWS:
+            raise NotImplementedError(f"pushed() is for the decode regime (M <= {self.PUSH_MAX_ROWS}); use gathered() for M={m}")
+        out_dtype = kwargs.get("output_dtype") or x.dtype
+        buf, _, peers = self._symmetric(m, out_dtype, x.device)
+        self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size,
+                   out=buf[self.rank], peer_out_ptrs=peers, **kwargs)  # fmt: skip
+        return buf
+
+    def pushed_local_view(self, m: int, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+        """This rank's own `[M, N/G]` slot of the symmetric gather buffer used by `pushed()`."""
+        return self._symm[(m, dtype)][0][self.rank]
+
+    def sync(self) -> None:
+        """Cross-GPU barrier on the current stream (device side, symmetric-memory signal pads): after it, everything the
+        peers pushed before THEIR sync() is visible here."""
+        if self.world == 1:
+            return
+        if not self._symm:
+            raise RuntimeError("sync() before any pushed() call")
+        next(iter(self._symm.values()))[1].barrier(channel=0)
 
     def __call__(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         """`[M, N]` on every rank, same values as the unsharded op."""

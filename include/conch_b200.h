@@ -91,6 +91,21 @@ CB200_API int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_
                  void* workspace, size_t workspace_bytes,
                  int variant, void* stream);
 
+/* Multi-GPU epilogue (no counterpart in the reference, which has no distributed code): cb200_mpgemm whose
+ * kernel ALSO stores the result into `num_peers` (<= 7) peer buffers -- peer_out[i] is a device pointer, valid in this
+ * process, to an [M, N] buffer of another GPU (CUDA IPC / symmetric memory): typically this rank's slot of every other
+ * rank's gather buffer, so an N-sharded layer needs no separate all-gather.  The stores are plain P2P writes over NVLink,
+ * visible to the peer once this kernel has completed; synchronising the ranks (one barrier per token, say) is the
+ * caller's job.  Decode kernel only: AUTO picks it for M <= 8 (M <= 16 on big matrices), variant = CB200_DECODE_MMA forces
+ * it for any M (16 rows per pass); any other choice returns CB200_ERR_UNSUPPORTED -- large outputs are bandwidth-bound and
+ * belong to an all-gather. */
+CB200_API int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
+                 int64_t M, int64_t K, int64_t N,
+                 int weight_size_bits, int weight_bias, int64_t group_size,
+                 int act_dtype, int out_dtype, int zp_kind, int zp_is_scalar,
+                 void* workspace, size_t workspace_bytes,
+                 int variant, void* stream, void* const* peer_out, int num_peers);
+
 /* Which kernel family the last cb200_mpgemm call on this thread dispatched to (a cb200_variant), and how many
  * kernel launches it enqueued.  Used by tests and by bench.py's `gpu_launches` accounting. */
 CB200_API int cb200_last_variant(void);

@@ -27,7 +27,7 @@ def _worker(rank: int, world: int, port: int, ret) -> None:
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        for m in (1, 16, 200):
+        for m in (1, 4, 16, 200):
             p = oracle.make_problem(m, 1024, 512, "uint4", 128, torch.float16, True, seed=m)
             x, wq, ws, wzp = (t.cuda() for t in (p.x, p.w_q_packed, p.w_s, p.w_zp))
             single = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128)
@@ -38,6 +38,19 @@ def _worker(rank: int, world: int, port: int, ret) -> None:
             assert torch.equal(out, single), f"sharded != single at M={m}"
             want = oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, 4, 0, 128)
             torch.testing.assert_close(out.cpu().float(), want.float(), rtol=1e-2, atol=1e-2)
+            if m <= ShardedMixedPrecisionLinear.PUSH_MAX_ROWS:
+                # fused gather: the decode kernel's epilogue stores into every rank's buffer (cb200_mpgemm_push), one barrier
+                buf = layer.pushed(x)
+                layer.sync()
+                torch.cuda.synchronize()
+                fused = buf.permute(1, 0, 2).reshape(m, -1)
+                assert torch.equal(fused, single), f"pushed != single at M={m}"
+                # a second round through the same symmetric buffer, different activations
+                layer.sync()  # nobody still reads round one
+                buf = layer.pushed(-x)
+                layer.sync()
+                torch.cuda.synchronize()
+                assert torch.equal(buf.permute(1, 0, 2).reshape(m, -1), mixed_precision_gemm(-x, wq, ws, wzp, 4, 0, 128))
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

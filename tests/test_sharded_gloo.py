@@ -45,6 +45,10 @@ def _worker(rank: int, world: int, port: int, m: int, wname: str, zp: bool, scal
         assert torch.equal(out, full)
         g = layer.gathered(p.x)
         assert g.shape == (world, m, 128) and torch.equal(g[1 - rank], full[:, (1 - rank) * 128 : (2 - rank) * 128])
+        ga, work = layer.gathered_async(p.x)  # enqueue only; the view is valid after the wait
+        assert work is not None
+        work.wait()
+        assert torch.equal(ga.permute(1, 0, 2).reshape(m, 256), full)
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
