@@ -55,7 +55,7 @@ def _signature(sources: list[pathlib.Path]) -> str:
 def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     sources = sorted(CSRC.glob("*.cu"))
     sig = _signature(sources)
-    stamp = OBJ / "signature.txt"
+    stamp = LIB.with_suffix(".so.sig")  # next to the library: the object directory does not travel to the GPU box
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == sig:
         return LIB
     nvcc = _nvcc()

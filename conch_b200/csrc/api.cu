@@ -192,10 +192,9 @@ int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, co
 
   int chosen = variant;
   if (chosen == CB200_AUTO) {
-    // regime split: HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x), tcgen05 pipeline above; 9..16 rows
-    // stay on the decode kernel only for big matrices, where its single launch beats the tcgen05 kernel's split-K
-    // pipeline (measured, profiles/r01_midm_probe.log)
-    const bool decode = M <= 8 || (M <= 16 && K * N > (int64_t(32) << 20));
+    // regime split: HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x), tcgen05 pipeline above (measured at
+    // M = 16: 10.7 vs 18.4 us on the 4096 x 4096 layer, 37 vs 61 us on 4096 x 28672 -- profiles/r01_midm_probe.log)
+    const bool decode = M <= 8;
     chosen = (decode || !tc_supported(p, weight_size_bits)) ? CB200_DECODE_MMA : CB200_TC_TS;
   }
   if (num_peers > 0 && chosen != CB200_DECODE_MMA) {

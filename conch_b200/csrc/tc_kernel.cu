@@ -8,10 +8,10 @@
 // (8 consecutive k of one column, conch/third_party/vllm/quant_utils.py:119-124) turns into one 16-byte K-major chunk,
 // (b) small M cheap (MMA-N = 16 instead of 112 wasted rows of a 128-row tile), (c) x a plain K-major TMA tile.
 //
-// Roles (640 threads):  warp 0 lane 0  TMA producer   (packed W tile, 8|16 rows x 128 int32, deep ring)
-//                       warp 3 lane 0  TMA producer   (x tile, 128B-swizzled; multicast across a cluster if enabled)
-//                       warp 1 lane 0  MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=m_tile, K=16)
-//                       warp 2         TMEM allocator
+// Roles (640 threads):  warp 0         TMA producer   (packed W tile, 8|16 rows x 128 int32, deep ring)
+//                       warp 3         TMA producer   (x tile, 128B-swizzled; multicast across a cluster if enabled)
+//                       warp 1         MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=m_tile, K=16)
+//                       warp 2         TMEM allocator; second MMA issuer (own accumulator) when m_tile <= 128
 //                       warps 4..19    dequant        (smem packed -> registers -> dequant_word() -> operand A): four
 //                                      SETS of four warps; set j owns stages j, j+4, ... (a thread = one weight column,
 //                                      all 64 k of the stage), so four stages are being dequantised concurrently and a
@@ -243,8 +243,12 @@ struct TcCfg {
   static constexpr int SA = TS ? 8 : 4;
   static constexpr int SX_FIT = (SMEM_BUDGET - SW * W_BYTES - SA * A_BYTES) / X_BYTES;
   static constexpr int SX = SX_FIT > SA ? SA : SX_FIT;   // <= SA: the x producer reuses the A ring's mma_done barriers
-  static constexpr int A_COL0 = MT;                     // first TMEM column of the A ring (TS)
-  static constexpr int TMEM_NEED = MT + (TS ? SA * 32 : 0);
+  // Two MMA issuers on two accumulators for the small tiles: below m_tile ~256 the kernel is bound by the ~55 cycles
+  // one thread needs per tcgen05.mma issue, not by the tensor pipe, so warps 1 and 2 take alternate rounds of K blocks
+  // into D0 / D1 (summed in the epilogue) and the issue rate doubles.
+  static constexpr bool DUAL = TS && MT <= 128;
+  static constexpr int A_COL0 = DUAL ? 2 * MT : MT;     // first TMEM column of the A ring (TS)
+  static constexpr int TMEM_NEED = A_COL0 + (TS ? SA * 32 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = SX * X_BYTES + SW * W_BYTES + SA * A_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers*/;
   static_assert(SX >= 3, "x ring too shallow");
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       mbar_init(a_ready(s), 4);
       mbar_init(mma_done(s), prm.cluster);  // every CTA of the cluster must have released the x slot (x is multicast)
     }
-    mbar_init(d_full, 1);
+    mbar_init(d_full, Cfg::DUAL ? 2 : 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -387,8 +391,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ==================================================================
+  } else if (warp == 1 || (Cfg::DUAL && warp == 2)) {
+    // ================================ MMA issuer(s) ===============================================================
     // The whole warp runs the loop convergently and ONE elected lane issues: with `elect.sync` the compiler emits
     // straight-line UTCHMMA code (a plain `lane == 0` branch makes it wrap every tcgen05 instruction in a
     // per-active-thread uniformisation loop, which made this issue loop -- not the tensor pipe -- the limiter).
@@ -397,9 +401,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // N>>3 at [17,23), M>>4 at [24,29)
     constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(MT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
     // UM K blocks per round: lanes poll the 2 UM barriers {x_full, a_ready} x {it .. it + UM - 1} concurrently.
-    constexpr int UM = (TS && MT <= 128) ? 4 : 2;  // must stay <= SX and well below SA (the rings must keep slack)
-    static_assert(UM <= SX && UM < SA || !TS, "MMA round larger than the rings");
-    for (int it = 0; it < nk; it += UM) {
+    constexpr int UM = 2;                        // (with two issuers, two rounds are in flight: 4 of the 8 A slots)
+    constexpr int NISS = Cfg::DUAL ? 2 : 1;      // issuers; issuer `who` takes rounds who, who + NISS, ...
+    static_assert(UM * NISS <= SX && UM * NISS < SA || !TS, "MMA rounds larger than the rings");
+    const int who = Cfg::DUAL ? warp - 1 : 0;
+    const uint32_t d_tmem = tmem_base + uint32_t(who * MT);  // this issuer's accumulator
+    const int it_first = who * UM;
+    for (int it = it_first; it < nk; it += UM * NISS) {
       const int nb = min(UM, nk - it);
       TRACE(2, it);
       {
@@ -421,12 +429,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const uint64_t bdesc = make_sw128_desc(x_base + sx * Cfg::X_BYTES);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {  // four K=16 MMAs per 64-wide K block: +32 bytes inside the swizzle atom
-              const uint32_t acc = (it | u | k4) != 0;
+              const uint32_t acc = ((it - it_first) | u | k4) != 0;
               if constexpr (TS) {
-                umma_ts(tmem_base, tmem_base + Cfg::A_COL0 + sa * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
+                umma_ts(d_tmem, tmem_base + Cfg::A_COL0 + sa * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
               } else {
                 const uint64_t adesc = make_sw128_desc(a_base + sa * Cfg::A_BYTES);
-                umma_ss(tmem_base, adesc + uint64_t(k4 * 2), bdesc + uint64_t(k4 * 2), idesc, acc);
+                umma_ss(d_tmem, adesc + uint64_t(k4 * 2), bdesc + uint64_t(k4 * 2), idesc, acc);
               }
             }
             // once these MMAs have read them: release the A slot, and the x slot in every CTA that multicasts into it
@@ -437,12 +445,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         }
-        if (it + nb == nk) umma_commit(d_full);
       }
       __syncwarp();
       TRACE(5, it);
       TRACE(12, it);
     }
+    // all of this issuer's MMAs retired -> its accumulator is final (arrives at once if it never issued any)
+    if (elect_one()) umma_commit(d_full);
+    __syncwarp();
   } else if (warp >= 4) {
     // ================================ dequant warps, then epilogue ==================================================
     const int q = warp & 3;            // TMEM lane quarter this warp may touch
@@ -546,12 +556,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + col0;
       if constexpr (CH == 32) tmem_ld32(taddr, r);
       if constexpr (CH == 16) tmem_ld16(taddr, r);
+      uint32_t r2[32];
+      const bool second = Cfg::DUAL && nk > 2;  // the second issuer's accumulator holds rounds 1, 3, ... (none if nk <= 2)
+      if (second) {
+        if constexpr (CH == 32) tmem_ld32(taddr + MT, r2);
+        if constexpr (CH == 16) tmem_ld16(taddr + MT, r2);
+      }
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const int m = m0 + col0 + c;
         if (m < p.M && n_ok) {
-          const float v = __uint_as_float(r[c]);
+          float v = __uint_as_float(r[c]);
+          if (second) v += __uint_as_float(r2[c]);
           if (split) {
             __stcg(part + size_t(m) * p.N + n, v);
           } else {

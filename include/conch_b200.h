@@ -96,7 +96,7 @@ CB200_API int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_
  * process, to an [M, N] buffer of another GPU (CUDA IPC / symmetric memory): typically this rank's slot of every other
  * rank's gather buffer, so an N-sharded layer needs no separate all-gather.  The stores are plain P2P writes over NVLink,
  * visible to the peer once this kernel has completed; synchronising the ranks (one barrier per token, say) is the
- * caller's job.  Decode kernel only: AUTO picks it for M <= 8 (M <= 16 on big matrices), variant = CB200_DECODE_MMA forces
+ * caller's job.  Decode kernel only: AUTO picks it for M <= 8, variant = CB200_DECODE_MMA forces
  * it for any M (16 rows per pass); any other choice returns CB200_ERR_UNSUPPORTED -- large outputs are bandwidth-bound and
  * belong to an all-gather. */
 CB200_API int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
