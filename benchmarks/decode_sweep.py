@@ -26,7 +26,7 @@ def main() -> None:
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default="gpurun_out/decode_sweep.jsonl")
     ap.add_argument("--shapes", default="o,qkv,down,gate_up")
-    ap.add_argument("--ms", default="1,4,16")
+    ap.add_argument("--ms", default="1,4,8")
     ap.add_argument("--wtype", default="uint4")
     ap.add_argument("--dtype", default="fp16")
     args = ap.parse_args()

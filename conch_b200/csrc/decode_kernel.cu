@@ -3,7 +3,9 @@
 // Replaces the reference's single 128x64x64 Triton tile (conch/kernels/quantization/gemm.py:136-145, 491-494),
 // which at M=1 launches N/64 CTAs with no split-K.  Design (B200):
 //   * one WARP owns one (32-column block) x (1/S of K) slab; S is a divisor of the batches per column chosen so that the
-//     whole grid is one co-resident wave.  Warps are completely independent: no __syncthreads, no shared state;
+//     whole grid is one co-resident wave.  Neighbouring warps take neighbouring column blocks of the same K slab, so a
+//     CTA's four warps share one staged copy of the activations (one __syncthreads, for that barrier's init); apart
+//     from that the warps are independent;
 //   * the packed weights are the only large stream: every lane keeps a rotating window of 2*U (= 8) 128-bit read-once
 //     loads (ld.global.nc, L1 no-allocate) in flight -- the register that held step j is re-loaded with step j + 2U as
 //     soon as it has been read -- so with ~24 resident warps per SM about 100 KB per SM is outstanding, which is what it
@@ -83,10 +85,12 @@ struct DecodeGeom {
   int total_warps;    // (N / 32) * S
   int bpg;            // batches per scale group (g / (U * STEP_K))
   int pdl;            // launched with programmatic stream serialization
-  int x_row_bytes;    // per-warp smem: bytes per staged x row (slab bytes + 64 B pad against bank conflicts)
+  int x_row_bytes;    // per-CTA smem: bytes per staged x row (slab bytes + 64 B pad against bank conflicts)
   int meta_row_bytes; // per-warp smem: bytes per group row (64 B of scales + zero-points)
   int ngroups;        // scale groups touched by one warp
-  int warp_smem;      // per-warp smem bytes (x rows + group rows + mbarrier)
+  int warp_smem;      // per-warp smem bytes (group rows + mbarrier)
+  int cta_x_bytes;    // per-CTA smem bytes of the shared x slab (the 4 warps of a CTA work on the same K slab)
+  int cb_padded;      // column blocks rounded up to a multiple of 4 (whole CTAs per slab; padding warps only sync)
 };
 
 template <class A>
@@ -136,15 +140,21 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   constexpr bool FZP = ZK == CB200_ZP_ACT;
 
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);  // (the grid is whole CTAs: total_warps is a multiple of 4)
   DEC_STAMP(0);
-  if (w >= geo.total_warps) return;
   const int g8 = lane >> 2, tig = lane & 3;
   const int M = geo.m_rows;
   const int N = p.N;
   const int S = geo.splits;
-  const int cb = w / S;               // column block
-  const int si = w - cb * S;          // slab index inside the column block
+  // neighbouring warps take neighbouring column blocks of the SAME K slab: the four warps of a CTA read 512 contiguous
+  // bytes of every packed row between them and share ONE staged copy of the slab's activations
+  const int C = N / CW;               // column blocks
+  const int si = w / geo.cb_padded;   // slab index inside the column block (the same for the whole CTA)
+  const int cb = w - si * geo.cb_padded;  // column block
+  if (cb >= C) {                      // padding warp (N / 32 not a multiple of 4): only takes part in the CTA barrier
+    __syncthreads();
+    return;
+  }
   const int nunits = geo.units_per_warp;
   const int nsteps = nunits * U;
   const int b0 = si * nunits;         // first batch of this warp
@@ -152,23 +162,6 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   const int col = cb * CW + VEC * g8; // first of this lane's four weight columns
   const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
 
-  // ---- per-warp shared memory: x slab [m_rows][x_row_bytes], group rows [ngroups][meta_row_bytes], one mbarrier -------------
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t wsm = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) + (threadIdx.x >> 5) * geo.warp_smem;
-  const uint32_t xs_base = wsm;
-  const uint32_t meta_base = wsm + M * geo.x_row_bytes;
-  const uint32_t bar = meta_base + geo.ngroups * geo.meta_row_bytes;
-  const int g0 = b0 / bpg;  // a slab either covers whole groups or lies inside one group
-  const int slab_k = nsteps * 4 * PF;
-  constexpr uint32_t ZROW = ZK == CB200_ZP_I32 ? 128u : ZK == CB200_ZP_U8 ? 32u : ZK == CB200_ZP_ACT ? 64u : 0u;  // 32 columns
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t total = uint32_t(M) * uint32_t(slab_k * 2) + uint32_t(geo.ngroups) * (64u + (zp_per_group ? ZROW : 0u));
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-  }
-  __syncwarp();
-  DEC_STAMP(1);
   // ---- weight window: WIN loads in flight before anything else (weights are static: legal before griddepcontrol.wait) ----
   const char* wp = reinterpret_cast<const char*>(p.wq + (size_t(b0) * (U * 4) + tig) * N + col);
   const size_t step_bytes = size_t(16) * N;  // 4 packed rows
@@ -185,28 +178,53 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   if (geo.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   DEC_STAMP(2);
 
-  auto bulk = [&](uint32_t dst, const void* src, uint32_t bytes) {
+  // ---- shared memory: ONE x slab [m_rows][x_row_bytes] per CTA, then per warp: group rows [ngroups][meta_row_bytes] + mbarrier,
+  //      then the CTA's x barrier -----------------------------------------------------------------------------------------------
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  const uint32_t xs_base = smem0;
+  const uint32_t meta_base = smem0 + geo.cta_x_bytes + (threadIdx.x >> 5) * geo.warp_smem;
+  const uint32_t bar = meta_base + geo.ngroups * geo.meta_row_bytes;
+  const uint32_t xbar = smem0 + geo.cta_x_bytes + 4 * geo.warp_smem;
+  const int g0 = b0 / bpg;  // a slab either covers whole groups or lies inside one group
+  const int slab_k = nsteps * 4 * PF;
+  constexpr uint32_t ZROW = ZK == CB200_ZP_I32 ? 128u : ZK == CB200_ZP_U8 ? 32u : ZK == CB200_ZP_ACT ? 64u : 0u;  // 32 columns
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t total = uint32_t(geo.ngroups) * (64u + (zp_per_group ? ZROW : 0u));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xbar), "r"(uint32_t(M) * uint32_t(slab_k * 2))
+                   : "memory");
+    }
+  }
+  __syncthreads();  // the x barrier is initialised for everybody (the only CTA-wide synchronisation of the kernel)
+  DEC_STAMP(1);
+
+  auto bulk = [&](uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
+                 "r"(bytes), "r"(mbar)
                  : "memory");
   };
   // scales / zero-points of this warp's 32 columns, one row per group (static data: legal before griddepcontrol.wait)
   for (int g = lane; g < geo.ngroups; g += 32) {
     const size_t idx = size_t(g0 + g) * N + cb * CW;
-    bulk(meta_base + g * geo.meta_row_bytes, reinterpret_cast<const A*>(p.s) + idx, 64u);
+    bulk(meta_base + g * geo.meta_row_bytes, reinterpret_cast<const A*>(p.s) + idx, 64u, bar);
     if (zp_per_group) {
       const size_t zes = ZK == CB200_ZP_I32 ? 4 : ZK == CB200_ZP_U8 ? 1 : 2;
-      bulk(meta_base + g * geo.meta_row_bytes + 64, reinterpret_cast<const char*>(p.zp) + idx * zes, ZROW);
+      bulk(meta_base + g * geo.meta_row_bytes + 64, reinterpret_cast<const char*>(p.zp) + idx * zes, ZROW, bar);
     }
   }
 
   DEC_STAMP(3);
   if (geo.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // x / out / workspace belong to the stream order
 
-  // activations: row m of x, columns [b0 * U * STEP_K, + slab_k), one bulk copy per row
-  if (lane < M) {
+  // activations: row m of x, columns [b0 * U * STEP_K, + slab_k), one bulk copy per row, ONCE per CTA (warp 0 always exists)
+  if (threadIdx.x < M) {
     bulk(xs_base + lane * geo.x_row_bytes, reinterpret_cast<const A*>(p.x) + size_t(lane) * p.K + size_t(b0) * (U * 4 * PF),
-         uint32_t(slab_k * 2));
+         uint32_t(slab_k * 2), xbar);
   }
   bool m_ok[MT];
   uint32_t lane_x[MT];  // + step * (4 * PF * 2)
@@ -217,12 +235,15 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
     lane_x[mt] = xs_base + (m_ok[mt] ? m : 0) * geo.x_row_bytes + tig * (PF * 2);
   }
   uint32_t meta_cur = meta_base;  // row of the current group
-  {  // wait for the staged operands (they landed long before the first weight load returns)
+  // wait for the staged operands (they landed long before the first weight load returns)
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const uint32_t mbar = which ? xbar : bar;
     uint32_t done = 0;
     while (!done) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                    : "=r"(done)
-                   : "r"(bar)
+                   : "r"(mbar)
                    : "memory");
     }
   }
@@ -488,7 +509,7 @@ struct DecodePlan {
   int bpg;             // batches per scale group
   int splits, units_per_warp, col_blocks, total_warps;
   int ctas_per_sm;
-  int x_row_bytes, meta_row_bytes, ngroups, warp_smem, max_units;
+  int x_row_bytes, meta_row_bytes, ngroups, warp_smem, max_units, cta_x_bytes, cta_smem, cb_padded;
   bool fused;
 };
 
@@ -508,14 +529,16 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
   pl.ctas_per_sm = pick(g_decode_tuning.warps_k, mrows > 8 ? 3 : (pl.fused ? 4 : 5));
   const int by_regs = pl.ctas_per_sm;
   const int zrow = 128;  // worst case (int32 zero-points) keeps the layout independent of the zero-point kind
+  // shared memory of one CTA: the x slab (shared by its 4 warps) + per warp the group rows and a barrier + the x barrier
   auto warp_smem_for = [&](int per) {
-    const int xrow = per * pl.u * step_k * 2 + 64;
     const int ng = (per + pl.bpg - 1) / pl.bpg;
-    return ((mrows * xrow + ng * (64 + zrow) + 8 + 127) / 128) * 128;
+    return ((ng * (64 + zrow) + 8 + 127) / 128) * 128;
   };
-  // per-warp staging budget bounds the slab: x rows (2 B per k per row) must fit ~8 KB (16 KB for the 16-row variant)
+  auto cta_x_for = [&](int per) { return ((mrows * (per * pl.u * step_k * 2 + 64) + 127) / 128) * 128; };
+  auto cta_smem_for = [&](int per) { return cta_x_for(per) + 4 * warp_smem_for(per) + 16; };
+  // the CTA's staging budget bounds the slab: x rows (2 B per k per row) within ~24 KB (48 KB for the 16-row variant)
   {
-    const int budget = mrows > 8 ? 16 * 1024 : 8 * 1024;
+    const int budget = mrows > 8 ? 48 * 1024 : 24 * 1024;
     int mu = budget / (mrows * 2 * pl.u * step_k);
     if (mu < 1) mu = 1;
     pl.max_units = mu;
@@ -536,10 +559,10 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
       best = sdiv;
       continue;
     }
-    int by_smem = (227 * 1024) / (4 * warp_smem_for(per) + 1024);
+    int by_smem = (227 * 1024) / (cta_smem_for(per) + 1024);
     if (by_smem > by_regs) by_smem = by_regs;
     const int64_t capacity = int64_t(148) * by_smem * 4;  // co-resident warps at this split
-    const int64_t warps = int64_t(pl.col_blocks) * sdiv;
+    const int64_t warps = int64_t((pl.col_blocks + 3) / 4 * 4) * sdiv;
     if (best_ok && warps > capacity && sdiv > 1) break;  // one co-resident wave (measured: more waves do not help)
     if (best_ok && per < 2 && sdiv > 1) break;
     best = sdiv;
@@ -547,11 +570,14 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
   }
   pl.splits = best;
   pl.units_per_warp = B / best;
-  pl.total_warps = pl.col_blocks * best;
+  pl.cb_padded = (pl.col_blocks + 3) / 4 * 4;  // whole CTAs per K slab
+  pl.total_warps = pl.cb_padded * best;
   pl.x_row_bytes = pl.units_per_warp * pl.u * step_k * 2 + 64;
   pl.meta_row_bytes = 64 + zrow;
   pl.ngroups = (pl.units_per_warp + pl.bpg - 1) / pl.bpg;
   pl.warp_smem = warp_smem_for(pl.units_per_warp);
+  pl.cta_x_bytes = cta_x_for(pl.units_per_warp);
+  pl.cta_smem = cta_smem_for(pl.units_per_warp);
   return pl;
 }
 
@@ -656,16 +682,18 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     geo.meta_row_bytes = pl.meta_row_bytes;
     geo.ngroups = pl.ngroups;
     geo.warp_smem = pl.warp_smem;
+    geo.cta_x_bytes = pl.cta_x_bytes;
+    geo.cb_padded = pl.cb_padded;
     const int blocks = (pl.total_warps + 3) / 4;
     float* wsp = ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES) : nullptr;
     unsigned* wsc = reinterpret_cast<unsigned*>(ws);
     int rc;
     if (act_dtype == CB200_F16) {
-      rc = bits == 4 ? launch_typed<__half, 4>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream)
-                     : launch_typed<__half, 8>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream);
+      rc = bits == 4 ? launch_typed<__half, 4>(pl.u, pl.fused, p, geo, blocks, size_t(pl.cta_smem), wsp, wsc, stream)
+                     : launch_typed<__half, 8>(pl.u, pl.fused, p, geo, blocks, size_t(pl.cta_smem), wsp, wsc, stream);
     } else {
-      rc = bits == 4 ? launch_typed<__nv_bfloat16, 4>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream)
-                     : launch_typed<__nv_bfloat16, 8>(pl.u, pl.fused, p, geo, blocks, size_t(4) * pl.warp_smem, wsp, wsc, stream);
+      rc = bits == 4 ? launch_typed<__nv_bfloat16, 4>(pl.u, pl.fused, p, geo, blocks, size_t(pl.cta_smem), wsp, wsc, stream)
+                     : launch_typed<__nv_bfloat16, 8>(pl.u, pl.fused, p, geo, blocks, size_t(pl.cta_smem), wsp, wsc, stream);
     }
     if (rc != 0) return rc;
     if (launches) ++*launches;
