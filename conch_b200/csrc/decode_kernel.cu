@@ -46,7 +46,8 @@
 //   until the window drains (+2.9 us), in front of it they push the window out of the load queue (~100 512-byte requests
 //   per SM is all the LSU tracks) -- hence the TMA bulk copies, which bypass that queue, at ~40 ns of issue time each.
 //   `prefetch.global.L2` running 1..16 iterations ahead of the window (to get more bytes in flight than that queue
-//   allows) made every layer 5-15% slower.  A stream-K variant (equal ranges of the linearised (column block, batch) space, every SM equally loaded) was built and
+//   allows) made every layer 5-15% slower, and so did a one-shot prefetch of the next 1-4 iterations issued before
+//   griddepcontrol.wait (meant to use the previous kernel's idle tail).  A stream-K variant (equal ranges of the linearised (column block, batch) space, every SM equally loaded) was built and
 //   measured: -8% on that layer, +8% on the smaller ones (second publish per straddling warp, longer prologue), no net
 //   gain on the bench -- not kept.
 #include "common.cuh"
