@@ -655,6 +655,9 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     p.x = reinterpret_cast<const char*>(p_in.x) + size_t(m0) * p_in.K * 2;
     const size_t out_es = p_in.out_dtype == CB200_F32 ? 4 : 2;
     p.out = reinterpret_cast<char*>(p_in.out) + size_t(m0) * p_in.N * out_es;
+    for (int i = 0; i < p_in.n_peers; ++i) {
+      p.peer_out[i] = reinterpret_cast<char*>(p_in.peer_out[i]) + size_t(m0) * p_in.N * out_es;
+    }
     p.M = mrows;
 
     const DecodePlan pl = decode_plan(mrows, p.K, p.N, bits, p.g);

@@ -364,3 +364,38 @@ def test_batch_rows_equal_single_rows():
     for i in (0, 5, 15):
         one = mixed_precision_gemm(x[i : i + 1].contiguous(), wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)
         torch.testing.assert_close(one[0], full[i], rtol=5e-3, atol=5e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# multi-GPU epilogue (cb200_mpgemm_push) exercised on ONE device: the "peers" are just other local buffers
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [1, 3, 8])
+@pytest.mark.parametrize("k,n", [(1024, 512), (4096, 6144)])
+def test_push_epilogue_writes_every_peer_buffer(m, k, n):
+    from conch_b200 import quant_utils
+
+    wq, ws, wzp = quant_utils.random_packed_weights(k, n, quant_utils.scalar_types.uint4, 128, torch.float16, "cuda", seed=11)
+    x = torch.randn((m, k), device="cuda", dtype=torch.float16)
+    plain = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128)
+    peers = [torch.full((m, n), float("nan"), device="cuda", dtype=torch.float16) for _ in range(3)]
+    out = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, peer_out_ptrs=[t.data_ptr() for t in peers])
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)
+    for t in peers:
+        assert torch.equal(t, plain)
+
+
+def test_push_epilogue_is_decode_only():
+    from conch_b200 import _lib, quant_utils
+
+    wq, ws, wzp = quant_utils.random_packed_weights(512, 256, quant_utils.scalar_types.uint4, 128, torch.float16, "cuda", seed=12)
+    x = torch.randn((64, 512), device="cuda", dtype=torch.float16)
+    peer = torch.empty((64, 256), device="cuda", dtype=torch.float16)
+    with pytest.raises(NotImplementedError):
+        mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, peer_out_ptrs=[peer.data_ptr()])  # AUTO -> tcgen05 kernel at M=64
+    with pytest.raises(ValueError):
+        mixed_precision_gemm(x[:1].contiguous(), wq, ws, wzp, 4, 0, 128, peer_out_ptrs=[peer.data_ptr()] * 8)  # > 7 peers
+    # forcing the decode kernel works for any M (16 rows per pass)
+    got = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.DECODE_MMA, peer_out_ptrs=[peer.data_ptr()])
+    torch.cuda.synchronize()
+    assert torch.equal(peer, got)
