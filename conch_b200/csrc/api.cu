@@ -210,7 +210,11 @@ int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, co
       set_error("tcgen05 variant %d does not support this problem", chosen);
       return CB200_ERR_UNSUPPORTED;
     }
-    rc = launch_tc(p, weight_size_bits, act_dtype, chosen, workspace, workspace_bytes, st, &launches);
+    if (chosen == CB200_TC2_TS) {
+      rc = launch_tc2(p, weight_size_bits, act_dtype, st, &launches);  // persistent, m_tile 128 (large M)
+    } else {
+      rc = launch_tc(p, weight_size_bits, act_dtype, chosen, workspace, workspace_bytes, st, &launches);
+    }
   } else {
     set_error("unknown variant %d", variant);
     return CB200_ERR_ARG;

@@ -49,6 +49,7 @@ int launch_decode(const Problem& p, int bits, int act_dtype, void* ws, size_t ws
 size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
 int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, size_t ws_bytes,
               cudaStream_t stream, int* launches);
+int launch_tc2(const Problem& p, int bits, int act_dtype, cudaStream_t stream, int* launches);
 size_t tc_workspace_bytes(int64_t M, int64_t K, int64_t N);
 bool tc_supported(const Problem& p, int bits);
 

@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "dequant.cuh"
+#include "tc_ptx.cuh"
 
 namespace cb200 {
 
@@ -37,174 +38,6 @@ int g_tc_cluster = 0;  // 0 = default (no cluster)
 long long* g_tc_trace = nullptr;
 extern "C" __attribute__((visibility("default"))) void cb200_debug_set_tc_trace(void* p) { g_tc_trace = reinterpret_cast<long long*>(p); }
 #endif
-
-// ------------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  // bounded spin: a protocol bug becomes a trap (launch error) instead of a hung GPU
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-// same, delivered to every CTA of the cluster whose bit is set in `mask` (same smem offset, same barrier offset in each)
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  __syncwarp();  // .aligned: the whole warp must arrive together (role code above is lane-divergent)
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// same, arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
-      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-      "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
-      "[%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile base 1024-byte aligned, 128-byte rows, 8-row atoms)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= uint64_t((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units            bits [0,14)
-  d |= uint64_t(1) << 16;                  // leading byte offset (unused for SW128 K-major)  [16,30)
-  d |= uint64_t(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B       bits [32,46)
-  d |= uint64_t(1) << 46;                  // descriptor version (sm_100)              bits [46,48)
-  d |= uint64_t(2) << 61;                  // layout type SWIZZLE_128B                 bits [61,64)
-  return d;
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // kernel
@@ -589,6 +422,298 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent variant (CB200_TC2_TS) for large M: m_tile 128, one CTA per SM walks the tiles t = blockIdx.x, + gridDim.x, ...
+// The W / A / x rings run on a K-block counter that does not stop at tile boundaries, so producers, dequant warps and the
+// MMA issuer roll straight into the next tile; the accumulator is double-buffered in TMEM (2 x 128 columns + the 8 x 32
+// column A ring = 512) and four dedicated epilogue warps drain tile j while the MMAs of tile j + 1 run.  What this removes
+// from the non-persistent kernel: TMEM allocation / barrier setup / pipeline fill per tile, the epilogue that nothing
+// overlapped, and most of the partial last wave (tiles are 128 x 128 instead of 128 x 256).
+// ------------------------------------------------------------------------------------------------------------------
+template <int BITS>
+struct Tc2Cfg {
+  static constexpr int MT = 128, NTILE = 128, KB = 64;
+  static constexpr int PF = 32 / BITS;
+  static constexpr int WROWS = KB / PF;
+  static constexpr int X_BYTES = MT * 128;
+  static constexpr int W_BYTES = WROWS * NTILE * 4;
+  static constexpr int SW = BITS == 4 ? 16 : 8;  // 64 KB
+  static constexpr int SA = 8;                   // 256 TMEM columns
+  static constexpr int SX = 8;                   // 128 KB
+  static constexpr int A_COL0 = 2 * MT;          // two accumulators first
+  static constexpr int SMEM_BYTES = SX * X_BYTES + SW * W_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers*/;
+};
+constexpr int kTc2Threads = 128 + 128 * kTcSets + 128;  // control warps, dequant warps, epilogue warps: 768
+
+struct Tc2Params {
+  Problem p;
+  int nk;          // K blocks per tile (K / 64)
+  int n_tiles;     // tiles along N
+  int total_tiles;
+  int gb;          // K blocks per quantisation group
+  int gb_shift;    // log2(gb) if gb is a power of two, else -1
+};
+
+template <class A, int BITS, int ZK>
+__global__ void __launch_bounds__(kTc2Threads, 1)
+    tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, Tc2Params prm) {
+  using Cfg = Tc2Cfg<BITS>;
+  constexpr int MT = Cfg::MT;
+  constexpr int SX = Cfg::SX, SW = Cfg::SW, SA = Cfg::SA;
+  constexpr bool FZP = ZK == CB200_ZP_ACT;
+  constexpr int PAIRS = 16 / BITS;
+  constexpr int WPT = 64 / Cfg::PF;
+  constexpr int SETS = kTcSets;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t x_base = smem_base;
+  const uint32_t w_base = x_base + SX * Cfg::X_BYTES;
+  const uint32_t bar_base = w_base + SW * Cfg::W_BYTES;
+  auto x_full = [&](int s) { return bar_base + 8u * s; };
+  auto w_full = [&](int s) { return bar_base + 8u * (SX + s); };
+  auto w_free = [&](int s) { return bar_base + 8u * (SX + SW + s); };
+  auto a_ready = [&](int s) { return bar_base + 8u * (SX + 2 * SW + s); };
+  auto mma_done = [&](int s) { return bar_base + 8u * (SX + 2 * SW + SA + s); };
+  auto d_full = [&](int b) { return bar_base + 8u * (SX + 2 * SW + 2 * SA + b); };
+  auto d_empty = [&](int b) { return bar_base + 8u * (SX + 2 * SW + 2 * SA + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (SX + 2 * SW + 2 * SA + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const Problem& p = prm.p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = prm.nk;
+  const int my_tiles = (prm.total_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int G = my_tiles * nk;  // K blocks this CTA walks through, tile after tile
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_w);
+    for (int s = 0; s < SX; ++s) mbar_init(x_full(s), 1);
+    for (int s = 0; s < SW; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_free(s), 4);
+    }
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(a_ready(s), 4);
+      mbar_init(mma_done(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(d_full(b), 1);
+      mbar_init(d_empty(b), 4);  // the four epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  // (tile, K block) cursor: K blocks are visited g = 0, 1, ... G-1; tile j = g / nk is t = blockIdx.x + j * gridDim.x
+  struct Cursor {
+    int j, kb, t;
+  };
+  auto advance = [&](Cursor& c, int by) {
+    c.kb += by;
+    while (c.kb >= nk) {
+      c.kb -= nk;
+      ++c.j;
+      c.t += int(gridDim.x);
+    }
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer: packed weights ==================================================
+    constexpr int UW = 4;
+    Cursor c{0, 0, int(blockIdx.x)};
+    for (int g = 0; g < G; g += UW) {
+      const int nb = min(UW, G - g);
+      {
+        int i = g + (lane & (UW - 1));
+        if (i >= G) i = g;
+        mbar_wait(w_free(i % SW), ((i / SW) & 1) ^ 1);
+      }
+      __syncwarp();
+      if (elect_one()) {
+        Cursor cc = c;
+        for (int u = 0; u < nb; ++u) {
+          const int s = (g + u) % SW;
+          mbar_expect_tx(w_full(s), Cfg::W_BYTES);
+          tma_load_2d(w_base + s * Cfg::W_BYTES, &tmap_w, (cc.t % prm.n_tiles) * Cfg::NTILE, cc.kb * Cfg::WROWS, w_full(s));
+          advance(cc, 1);
+        }
+      }
+      __syncwarp();
+      advance(c, nb);
+    }
+  } else if (warp == 3) {
+    // ================================ TMA producer: activations =====================================================
+    constexpr int UX = 2;
+    Cursor c{0, 0, int(blockIdx.x)};
+    for (int g = 0; g < G; g += UX) {
+      const int nb = min(UX, G - g);
+      {
+        int i = g + (lane & (UX - 1));
+        if (i >= G) i = g;
+        if (i >= SX) {
+          const int q = i - SX;
+          mbar_wait(mma_done(q % SA), (q / SA) & 1);
+        }
+      }
+      __syncwarp();
+      if (elect_one()) {
+        Cursor cc = c;
+        for (int u = 0; u < nb; ++u) {
+          const int s = (g + u) % SX;
+          mbar_expect_tx(x_full(s), Cfg::X_BYTES);
+          tma_load_2d(x_base + s * Cfg::X_BYTES, &tmap_x, cc.kb * Cfg::KB, (cc.t / prm.n_tiles) * MT, x_full(s));
+          advance(cc, 1);
+        }
+      }
+      __syncwarp();
+      advance(c, nb);
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================================================
+    constexpr uint32_t fmt = std::is_same<A, __half>::value ? 0u : 1u;
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(MT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    constexpr int UM = 4;
+    Cursor c{0, 0, int(blockIdx.x)};
+    for (int g = 0; g < G; g += UM) {
+      const int nb = min(UM, G - g);
+      {
+        const int l = lane & (2 * UM - 1);
+        int i = g + (l >> 1);
+        if (i >= G) i = g;
+        const uint32_t bar = (l & 1) ? a_ready(i % SA) : x_full(i % SX);
+        const uint32_t par = uint32_t((l & 1) ? (i / SA) : (i / SX)) & 1u;
+        mbar_wait(bar, par);
+      }
+      __syncwarp();
+      tc_fence_after();
+      if (elect_one()) {
+        Cursor cc = c;
+        for (int u = 0; u < nb; ++u) {
+          const int sx = (g + u) % SX, sa = (g + u) % SA;
+          const int buf = cc.j & 1;
+          if (cc.kb == 0) {  // first K block of a tile: its accumulator must have been drained (tile j - 2)
+            mbar_wait(d_empty(buf), ((cc.j >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t d_tmem = tmem_base + uint32_t(buf * MT);
+          const uint64_t bdesc = make_sw128_desc(x_base + sx * Cfg::X_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t acc = (cc.kb | k4) != 0;
+            umma_ts(d_tmem, tmem_base + Cfg::A_COL0 + sa * 32 + k4 * 8, bdesc + uint64_t(k4 * 2), idesc, acc);
+          }
+          umma_commit(mma_done(sa));
+          if (cc.kb == nk - 1) umma_commit(d_full(buf));  // the tile's accumulator is complete once these retire
+          advance(cc, 1);
+        }
+      }
+      __syncwarp();
+      advance(c, nb);
+    }
+  } else if (warp >= 4 && warp < 4 + 4 * SETS) {
+    // ================================ dequant warps ==================================================================
+    const int q = warp & 3;
+    const int set = (warp - 4) >> 2;
+    const int nl = q * 32 + lane;
+    const A* sp = reinterpret_cast<const A*>(p.s);
+    A raw_s = A(0.f), raw_zf = A(0.f);
+    int raw_z = 0;
+    int zscalar = 0;
+    A zfscalar = A(0.f);
+    if (ZK != CB200_ZP_NONE && p.zp_scalar) {
+      if constexpr (ZK == CB200_ZP_I32) zscalar = __ldg(reinterpret_cast<const int32_t*>(p.zp));
+      if constexpr (ZK == CB200_ZP_U8) zscalar = __ldg(reinterpret_cast<const uint8_t*>(p.zp));
+      if constexpr (ZK == CB200_ZP_ACT) zfscalar = *reinterpret_cast<const A*>(p.zp);
+    }
+    const bool zp_per_group = ZK != CB200_ZP_NONE && !p.zp_scalar;
+    int n_col = 0;  // this thread's weight column in the cursor's tile (recomputed only when the tile changes)
+    auto fetch_meta = [&](const Cursor& c) {  // scale / zero-point of this thread's column for K block c.kb of tile c.t
+      raw_z = zscalar;
+      raw_zf = zfscalar;
+      const int n = n_col;
+      if (c.j < my_tiles && n < p.N) {
+        const int grp = prm.gb_shift >= 0 ? (c.kb >> prm.gb_shift) : (c.kb / prm.gb);
+        const size_t idx = size_t(grp) * p.N + n;
+        raw_s = sp[idx];
+        if (zp_per_group) {
+          if constexpr (ZK == CB200_ZP_I32) raw_z = __ldg(reinterpret_cast<const int32_t*>(p.zp) + idx);
+          if constexpr (ZK == CB200_ZP_U8) raw_z = __ldg(reinterpret_cast<const uint8_t*>(p.zp) + idx);
+          if constexpr (ZK == CB200_ZP_ACT) raw_zf = reinterpret_cast<const A*>(p.zp)[idx];
+        }
+      }
+    };
+    Cursor c{0, 0, int(blockIdx.x)};
+    advance(c, set);
+    n_col = (c.t % prm.n_tiles) * Cfg::NTILE + nl;
+    fetch_meta(c);
+    for (int g = set; g < G; g += SETS) {
+      const int sw = g % SW, sa = g % SA;
+      const ColQ cq = make_colq<A, BITS, Order::Natural, FZP>(raw_s, float(raw_z + p.bias), raw_zf);
+      const int j_before = c.j;
+      advance(c, SETS);
+      if (c.j != j_before) n_col = (c.t % prm.n_tiles) * Cfg::NTILE + nl;
+      fetch_meta(c);  // for this set's next K block; consumed one full iteration later
+      mbar_wait(w_full(sw), (g / SW) & 1);
+      const uint32_t* wst = reinterpret_cast<const uint32_t*>(smem_gen + (w_base - smem_base) + sw * Cfg::W_BYTES);
+      uint32_t regs[32];
+#pragma unroll
+      for (int j = 0; j < WPT; ++j) {
+        const uint32_t word = wst[j * Cfg::NTILE + nl];
+        uint32_t pr[PAIRS];
+        dequant_word<A, BITS, Order::Natural, FZP>(word, cq, pr);
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) regs[j * PAIRS + i] = pr[i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_free(sw));
+      mbar_wait(mma_done(sa), ((g / SA) & 1) ^ 1);
+      tc_fence_after();
+      tmem_st32(tmem_base + (uint32_t(q * 32) << 16) + Cfg::A_COL0 + sa * 32, regs);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready(sa));
+    }
+  } else if (warp >= 4 + 4 * SETS) {
+    // ================================ epilogue warps: drain tile j while tile j + 1 is being multiplied ==============
+    const int q = warp & 3;  // TMEM lane quarter (warp 20 -> 0)
+    const int nl = q * 32 + lane;
+    int t = int(blockIdx.x);
+    for (int j = 0; j < my_tiles; ++j, t += int(gridDim.x)) {
+      const int buf = j & 1;
+      const int n = (t % prm.n_tiles) * Cfg::NTILE + nl;
+      const int m0 = (t / prm.n_tiles) * MT;
+      const bool n_ok = n < p.N;
+      mbar_wait(d_full(buf), (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int col0 = 0; col0 < MT; col0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * MT + col0), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cidx = 0; cidx < 32; ++cidx) {
+          const int m = m0 + col0 + cidx;
+          if (m < p.M && n_ok) store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, __uint_as_float(r[cidx]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 // out[m, n] = cast(sum_z partial[z][m][n]) -- all SMs in parallel (measured faster than a last-CTA fix-up here: the
 // partial planes are M x N fp32, far more than one CTA can sum quickly)
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t total4, int splits,
@@ -711,29 +836,15 @@ static int launch_mt(int mt, const CUtensorMap& mx, const CUtensorMap& mw, const
   }
 }
 
-int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, size_t ws_bytes, cudaStream_t stream,
-              int* launches) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled driver entry point not available");
-    return CB200_ERR_DEVICE;
-  }
-  const TcPlan pl = tc_plan(p.M, p.K, p.N);
-  const int mt = pl.m_tile;
+// x: [M, K] row-major, box {64, x_box_rows}, 128-byte swizzle; packed W: [K/pf, N] int32, box {128, 64/pf}
+static int make_tmaps(EncodeTiledFn enc, const Problem& p, int bits, int act_dtype, int x_box_rows, CUtensorMap& mx,
+                      CUtensorMap& mw) {
   const int pf = 32 / bits;
-  // Optional (cb200_set_tc_cluster): CTAs with neighbouring n tiles and the same m tile share the x tile -- each fetches
-  // 1/cluster of it and multicasts.  Measured neutral (2) to slightly slower (4) on every prefill shape: the x traffic
-  // from L2 is not what limits this kernel, so the default is no cluster.
-  const int n_tiles = (p.N + 127) / 128;
-  int cluster = g_tc_cluster > 0 ? g_tc_cluster : 1;
-  while (cluster > 1 && (n_tiles % cluster != 0 || mt / cluster < 8)) cluster /= 2;
-
   // x: [M, K] row-major -> dims {K, M}, box {64, m_tile}, 128-byte swizzle; rows beyond M are zero-filled by TMA
-  CUtensorMap mx, mw;
   {
     const cuuint64_t dims[2] = {cuuint64_t(p.K), cuuint64_t(p.M)};
     const cuuint64_t strides[1] = {cuuint64_t(p.K) * 2};
-    const cuuint32_t box[2] = {64, cuuint32_t(mt / cluster)};
+    const cuuint32_t box[2] = {64, cuuint32_t(x_box_rows)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&mx, act_dtype == CB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                            const_cast<void*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -757,6 +868,28 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
       return CB200_ERR_ARG;
     }
   }
+
+  return 0;
+}
+
+int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, size_t ws_bytes, cudaStream_t stream,
+              int* launches) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return CB200_ERR_DEVICE;
+  }
+  const TcPlan pl = tc_plan(p.M, p.K, p.N);
+  const int mt = pl.m_tile;
+  // Optional (cb200_set_tc_cluster): CTAs with neighbouring n tiles and the same m tile share the x tile -- each fetches
+  // 1/cluster of it and multicasts.  Measured neutral (2) to slightly slower (4) on every prefill shape: the x traffic
+  // from L2 is not what limits this kernel, so the default is no cluster.
+  const int n_tiles = (p.N + 127) / 128;
+  int cluster = g_tc_cluster > 0 ? g_tc_cluster : 1;
+  while (cluster > 1 && (n_tiles % cluster != 0 || mt / cluster < 8)) cluster /= 2;
+
+  CUtensorMap mx, mw;
+  if (int rc = make_tmaps(enc, p, bits, act_dtype, mt / cluster, mx, mw)) return rc;
 
   TcParams prm;
   prm.p = p;
@@ -798,6 +931,59 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
     CB200_CUDA_CHECK(cudaGetLastError());
     if (launches) ++*launches;
   }
+  return 0;
+}
+
+// ---- persistent variant ---------------------------------------------------------------------------------------------
+template <class A, int BITS>
+static int launch_tc2_zk(const CUtensorMap& mx, const CUtensorMap& mw, const Tc2Params& prm, int ctas, cudaStream_t stream) {
+  void (*kern)(const CUtensorMap, const CUtensorMap, Tc2Params);
+  switch (prm.p.zp_kind) {
+    case CB200_ZP_NONE: kern = tc2_kernel<A, BITS, CB200_ZP_NONE>; break;
+    case CB200_ZP_I32: kern = tc2_kernel<A, BITS, CB200_ZP_I32>; break;
+    case CB200_ZP_U8: kern = tc2_kernel<A, BITS, CB200_ZP_U8>; break;
+    default: kern = tc2_kernel<A, BITS, CB200_ZP_ACT>; break;
+  }
+  CB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<BITS>::SMEM_BYTES));
+  kern<<<ctas, kTc2Threads, Tc2Cfg<BITS>::SMEM_BYTES, stream>>>(mx, mw, prm);
+  CB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_tc2(const Problem& p, int bits, int act_dtype, cudaStream_t stream, int* launches) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return CB200_ERR_DEVICE;
+  }
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    CB200_CUDA_CHECK(cudaGetDevice(&dev));
+    CB200_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  CUtensorMap mx, mw;
+  if (int rc = make_tmaps(enc, p, bits, act_dtype, 128, mx, mw)) return rc;
+  Tc2Params prm;
+  prm.p = p;
+  prm.nk = p.K / 64;
+  prm.n_tiles = (p.N + 127) / 128;
+  prm.total_tiles = prm.n_tiles * ((p.M + 127) / 128);
+  prm.gb = p.g / 64;
+  prm.gb_shift = -1;
+  for (int sh = 0; sh < 31; ++sh) {
+    if ((1 << sh) == prm.gb) prm.gb_shift = sh;
+  }
+  const int ctas = prm.total_tiles < sm_count ? prm.total_tiles : sm_count;  // one persistent CTA per SM
+  int rc;
+  if (act_dtype == CB200_F16) {
+    rc = bits == 4 ? launch_tc2_zk<__half, 4>(mx, mw, prm, ctas, stream) : launch_tc2_zk<__half, 8>(mx, mw, prm, ctas, stream);
+  } else {
+    rc = bits == 4 ? launch_tc2_zk<__nv_bfloat16, 4>(mx, mw, prm, ctas, stream)
+                   : launch_tc2_zk<__nv_bfloat16, 8>(mx, mw, prm, ctas, stream);
+  }
+  if (rc) return rc;
+  if (launches) ++*launches;
   return 0;
 }
 

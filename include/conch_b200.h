@@ -58,7 +58,7 @@ enum cb200_variant {
   CB200_DECODE_MMA = 1,   /* M <= 16 per pass: split-K skinny GEMM, 64/128-bit weight loads, in-register dequant, HMMA dot, smem + last-CTA reduce */
   CB200_TC_SS = 2,        /* tcgen05: TMA -> smem dequant (K-major, 128B swizzle) -> UMMA (both operands smem), TMEM accumulators */
   CB200_TC_TS = 3,        /* tcgen05: TMA -> dequant straight into TMEM (W is the TMEM A operand), x tile from smem */
-  CB200_TC2_TS = 4        /* as TC_TS on a 2-CTA pair (cta_group::2), persistent */
+  CB200_TC2_TS = 4        /* persistent tcgen05 kernel: m_tile 128, two TMEM accumulators, epilogue overlaps the next tile */
 };
 
 enum cb200_status {

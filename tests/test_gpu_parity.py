@@ -399,3 +399,28 @@ def test_push_epilogue_is_decode_only():
     got = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.DECODE_MMA, peer_out_ptrs=[peer.data_ptr()])
     torch.cuda.synchronize()
     assert torch.equal(peer, got)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# persistent tcgen05 variant (CB200_TC2_TS): several tiles per CTA, double-buffered TMEM accumulators
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,k,n", [(1, 512, 256), (128, 512, 256), (300, 1024, 320), (1000, 2048, 1024), (4096, 1024, 6144)])
+@pytest.mark.parametrize("dtype,wname,zp,g", [(torch.float16, "uint4", True, 128), (torch.bfloat16, "uint4b8", False, 64),
+                                              (torch.float16, "uint8", True, -1), (torch.bfloat16, "uint8b128", False, 256)])
+def test_tc2_persistent_variant(m, k, n, dtype, wname, zp, g):
+    # (4096, 1024, 6144) is 32 x 48 = 1536 tiles: ~10 tiles per CTA through both accumulator buffers
+    _run_case(m, k, n, wname, g, dtype, zp, variant=_lib.TC2_TS)
+
+
+def test_tc2_matches_tc_ts_bit_for_bit_and_repeats():
+    from conch_b200 import quant_utils
+
+    k, n = 4096, 4096
+    wq, ws, wzp = quant_utils.random_packed_weights(k, n, quant_utils.scalar_types.uint4, 128, torch.float16, "cuda", seed=21)
+    x = torch.randn((2048, k), device="cuda", dtype=torch.float16)
+    a = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.TC2_TS)
+    b = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.TC2_TS)
+    ref = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=_lib.TC_TS)
+    assert torch.equal(a, b)
+    # same K order, one accumulator per tile in both kernels (TC_TS splits K over two accumulators only for m_tile <= 128)
+    assert torch.equal(a, ref)
