@@ -185,7 +185,7 @@ def mixed_precision_gemm(
 
     Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus three optional keywords:
     `variant` forces a kernel family (debug / benchmarking), `out` reuses a caller-owned output buffer, `peer_out_ptrs`
-    (multi-GPU, M <= 16) lists peer-GPU buffers the kernel also stores the result to (conch_b200/sharded.py).
+    (multi-GPU, decode regime: M <= 8) lists peer-GPU buffers the kernel also stores the result to (conch_b200/sharded.py).
     """
     _require_device(x, w_q_packed, w_s, w_zp)
     metadata = create_mixed_precision_metadata(

@@ -55,7 +55,7 @@ enum cb200_zp_kind { CB200_ZP_NONE = 0, CB200_ZP_I32 = 1, CB200_ZP_U8 = 2, CB200
 /* kernel families; 0 lets the library choose by regime */
 enum cb200_variant {
   CB200_AUTO = 0,
-  CB200_DECODE_MMA = 1,   /* M <= 16 per pass: split-K skinny GEMM, 64/128-bit weight loads, in-register dequant, HMMA dot, smem + last-CTA reduce */
+  CB200_DECODE_MMA = 1,   /* <= 16 rows per pass (AUTO: M <= 8): split-K skinny GEMM, 128-bit weight loads, in-register unpack, HMMA dot, last-arriver reduce */
   CB200_TC_SS = 2,        /* tcgen05: TMA -> smem dequant (K-major, 128B swizzle) -> UMMA (both operands smem), TMEM accumulators */
   CB200_TC_TS = 3,        /* tcgen05: TMA -> dequant straight into TMEM (W is the TMEM A operand), x tile from smem */
   CB200_TC2_TS = 4        /* persistent tcgen05 kernel: m_tile 128, two TMEM accumulators, epilogue overlaps the next tile */
