@@ -29,11 +29,16 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint3
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(mask), "r"(orv));  // (a & mask) | orv
   return r;
 }
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
+// (the intrinsic, not inline asm with an "r" selector: with a compile-time selector ptxas then encodes it as an immediate
+//  instead of moving it into a register before every PRMT -- 32 wasted instructions per 64-deep K block and thread)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+
+// Magic-number bytes for PRMT, deliberately NOT compile-time constants: SASS PRMT takes either the selector or the second
+// source as an immediate, not both.  With a literal second source ptxas keeps the (compile-time) selectors in registers and
+// re-materialises one before EVERY PRMT -- 32 wasted moves per 64-deep K block and thread in the tcgen05 dequant loop.
+// Read from the constant bank, the magic is a plain operand and the selector becomes the immediate.
+static __constant__ uint32_t kMagic64 = 0x64646464u;  // fp16: 0x64 next to a payload byte = 1024 + payload
+static __constant__ uint32_t kMagic4B = 0x4B000000u;  // fp32: 2^23 + payload
 
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
@@ -140,7 +145,7 @@ __device__ __forceinline__ void dequant_word_core(uint32_t w, const ColQ& c, uin
     const uint32_t one_sixteenth = 0x2C003C00u;  // (1.0, 1/16)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint32_t b = prmt(w, 0x64646464u, 0x4040u + 0x0101u * i);
+      const uint32_t b = prmt(w, kMagic64, 0x4040u + 0x0101u * i);
       const uint32_t p = b & 0x64f0640fu;
       uint32_t v = Ops::fma(p, one_sixteenth, c.c0);
       if constexpr (FZP) v = Ops::sub(v, c.zf);
@@ -149,7 +154,7 @@ __device__ __forceinline__ void dequant_word_core(uint32_t w, const ColQ& c, uin
   } else if constexpr (std::is_same<A, __half>::value && BITS == 8) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const uint32_t p = prmt(w, 0x64646464u, i == 0 ? 0x4140u : 0x4342u);  // (1024+k_2i, 1024+k_2i+1)
+      const uint32_t p = prmt(w, kMagic64, i == 0 ? 0x4140u : 0x4342u);  // (1024+k_2i, 1024+k_2i+1)
       uint32_t v = Ops::sub(p, c.c0);
       if constexpr (FZP) v = Ops::sub(v, c.zf);
       out[i] = Ops::mul(v, c.s);
@@ -182,7 +187,7 @@ __device__ __forceinline__ void dequant_word_core(uint32_t w, const ColQ& c, uin
     float f[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint32_t b = prmt(w, 0x4B000000u, 0x7540u + i);
+      const uint32_t b = prmt(w, kMagic4B, 0x7540u + i);
       f[i] = __uint_as_float(b) - __uint_as_float(c.c0);
     }
     if constexpr (FZP) {

@@ -341,10 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
       for (int j = 0; j < WPT; ++j) {
         const uint32_t word = wst[j * Cfg::NTILE + nl];
-        uint32_t pr[PAIRS];
-        dequant_word<A, BITS, Order::Natural, FZP>(word, cq, pr);
-#pragma unroll
-        for (int i = 0; i < PAIRS; ++i) regs[j * PAIRS + i] = pr[i];
+        dequant_word<A, BITS, Order::Natural, FZP>(word, cq, *reinterpret_cast<uint32_t(*)[PAIRS]>(&regs[j * PAIRS]));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(w_free(sw));  // the packed tile is in registers: the producer may refill the slot
@@ -665,10 +662,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1)
 #pragma unroll
       for (int j = 0; j < WPT; ++j) {
         const uint32_t word = wst[j * Cfg::NTILE + nl];
-        uint32_t pr[PAIRS];
-        dequant_word<A, BITS, Order::Natural, FZP>(word, cq, pr);
-#pragma unroll
-        for (int i = 0; i < PAIRS; ++i) regs[j * PAIRS + i] = pr[i];
+        dequant_word<A, BITS, Order::Natural, FZP>(word, cq, *reinterpret_cast<uint32_t(*)[PAIRS]>(&regs[j * PAIRS]));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(w_free(sw));
