@@ -45,8 +45,13 @@ extern "C" __attribute__((visibility("default"))) void cb200_debug_set_tc_trace(
 struct TcParams {
   Problem p;
   int kblocks_total;   // K / 64
-  int kb_per_split;    // 64-wide K blocks per CTA along gridDim.z
-  float* ws_partial;   // [split][M][N] fp32 when gridDim.z > 1
+  // 1-D grid of work items: items [0, t_full) are whole tiles (n fastest); the remaining t_tail tiles -- the partial last
+  // wave, or all tiles when there are too few to fill the GPU -- are split `splits` ways along K and come last, split-major
+  // (item t_full + z * t_tail + i = K slice z of tile t_full + i), so the last wave keeps every SM busy.
+  int n_tiles;         // tiles along N
+  int t_full, t_tail, splits;
+  int kb_per_split;    // 64-wide K blocks per K slice
+  float* ws_partial;   // [splits][t_tail][m_tile][128] fp32, tile-local
   int cluster;         // CTAs per cluster along n (1, 2 or 4): they share one x tile through TMA multicast
 #ifdef CB200_TC_TRACE
   long long* trace;    // [K/64][16] clock64 stamps of CTA (0,0,0) (debug builds only)
@@ -119,10 +124,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   const Problem& p = prm.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * Cfg::NTILE;
-  const int m0 = blockIdx.y * MT;
-  const int kb0 = blockIdx.z * prm.kb_per_split;
-  const int kb1 = min(kb0 + prm.kb_per_split, prm.kblocks_total);
+  int tile = int(blockIdx.x), zsplit = 0;
+  const bool split = int(blockIdx.x) >= prm.t_full && prm.splits > 1;
+  if (int(blockIdx.x) >= prm.t_full) {
+    const int r = int(blockIdx.x) - prm.t_full;
+    zsplit = r / prm.t_tail;
+    tile = prm.t_full + (r - zsplit * prm.t_tail);
+  }
+  const int n0 = (tile % prm.n_tiles) * Cfg::NTILE;
+  const int m0 = (tile / prm.n_tiles) * MT;
+  const int kb0 = split ? zsplit * prm.kb_per_split : 0;
+  const int kb1 = split ? min(kb0 + prm.kb_per_split, prm.kblocks_total) : prm.kblocks_total;
   const int nk = kb1 - kb0;
 
   // ---- one-time setup ------------------------------------------------------------------------------------------
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint16_t cmask = uint16_t((1u << prm.cluster) - 1u);
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 #ifdef CB200_TC_TRACE
-  const bool tracing = prm.trace && blockIdx.x == 7 && blockIdx.y == 1 && blockIdx.z == 0;
+  const bool tracing = prm.trace && int(blockIdx.x) == 7 + prm.n_tiles;
 #define TRACE(slot, it) do { if (tracing) prm.trace[(it) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TRACE(slot, it) do { } while (0)
@@ -377,8 +389,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     constexpr int ESETS = MT >= 64 ? SETS : (MT / 16);  // sets taking part in the epilogue (>= 16 columns per warp)
     constexpr int EC = MT / ESETS;                      // columns (m) handled by this warp
     constexpr int CH = EC >= 32 ? 32 : EC;              // columns per tcgen05.ld
-    const bool split = gridDim.z > 1;
-    float* part = split ? prm.ws_partial + size_t(blockIdx.z) * p.M * p.N : nullptr;
+    float* part = split ? prm.ws_partial + (size_t(zsplit) * prm.t_tail + size_t(tile - prm.t_full)) * (MT * Cfg::NTILE) : nullptr;
 #pragma unroll 1
     for (int cb = 0; cb < (set < ESETS ? EC : 0); cb += CH) {
       const int col0 = set * EC + cb;
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           float v = __uint_as_float(r[c]);
           if (second) v += __uint_as_float(r2[c]);
           if (split) {
-            __stcg(part + size_t(m) * p.N + n, v);
+            __stcg(part + (col0 + c) * Cfg::NTILE + nl, v);  // tile-local [m][n]: 128 contiguous bytes per warp store
           } else {
             store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, v);
           }
@@ -708,10 +719,12 @@ __global__ void __launch_bounds__(kTc2Threads, 1)
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-// out[m, n] = cast(sum_z partial[z][m][n]) -- all SMs in parallel (measured faster than a last-CTA fix-up here: the
-// partial planes are M x N fp32, far more than one CTA can sum quickly)
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t total4, int splits,
-                                     int out_dtype) {
+// out tile = cast(sum_z partial[z][tile][m][n]) for the split tiles -- all SMs in parallel (measured faster than a last-CTA
+// fix-up: the partial planes are far more than one CTA can sum quickly)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, Problem p, int mt, int n_tiles, int t_full, int t_tail,
+                                     int splits) {
+  const int per_tile4 = mt * 32;  // float4 per tile (128 columns)
+  const int64_t total4 = int64_t(t_tail) * per_tile4;
   const float4* p4 = reinterpret_cast<const float4*>(part);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
     float4 v = __ldcg(p4 + i);
@@ -719,10 +732,17 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, void* __res
       const float4 t = __ldcg(p4 + size_t(z) * total4 + i);
       v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
     }
-    store_out<float>(out, out_dtype, size_t(4 * i + 0), v.x);
-    store_out<float>(out, out_dtype, size_t(4 * i + 1), v.y);
-    store_out<float>(out, out_dtype, size_t(4 * i + 2), v.z);
-    store_out<float>(out, out_dtype, size_t(4 * i + 3), v.w);
+    const int tl = int(i / per_tile4), rem = int(i - int64_t(tl) * per_tile4);
+    const int tile = t_full + tl;
+    const int m = (tile / n_tiles) * mt + (rem >> 5);
+    const int n = (tile % n_tiles) * 128 + (rem & 31) * 4;
+    if (m < p.M && n < p.N) {  // N % 64 == 0: a group of four columns is inside or outside as a whole
+      const size_t o = size_t(m) * p.N + n;
+      store_out<float>(p.out, p.out_dtype, o + 0, v.x);
+      store_out<float>(p.out, p.out_dtype, o + 1, v.y);
+      store_out<float>(p.out, p.out_dtype, o + 2, v.z);
+      store_out<float>(p.out, p.out_dtype, o + 3, v.w);
+    }
   }
 }
 
@@ -748,8 +768,20 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct TcPlan {
-  int m_tile, split_k, kb_per_split;
+  int m_tile, n_tiles, tiles;
+  int t_full, t_tail, splits, kb_per_split;
 };
+
+static int tc_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      sms = 148;
+    }
+  }
+  return sms;
+}
 
 static TcPlan tc_plan(int M, int K, int N) {
   TcPlan pl;
@@ -759,18 +791,41 @@ static TcPlan tc_plan(int M, int K, int N) {
   }
   pl.m_tile = mt;
   const int kblocks = K / 64;
-  const int tiles = ((N + 127) / 128) * ((M + mt - 1) / mt);
+  const int sms = tc_sm_count();
+  pl.n_tiles = (N + 127) / 128;
+  pl.tiles = pl.n_tiles * ((M + mt - 1) / mt);
+  pl.t_full = pl.tiles;  // default: no split
+  pl.t_tail = 0;
   int ks = 1;
-  if (g_tc_tuning.split_k > 0) {
+  if (g_tc_tuning.split_k > 0) {  // forced: every tile split
     ks = g_tc_tuning.split_k;
-  } else if (tiles <= 74) {
-    ks = 148 / tiles;                         // exactly one wave of CTAs (never spill into a second one)
+    pl.t_full = 0;
+  } else if (pl.tiles <= sms / 2) {  // too few tiles to fill the GPU: split all of them, exactly one wave
+    ks = sms / pl.tiles;
     while (ks > 1 && kblocks / ks < 4) --ks;  // keep at least four K blocks per CTA
+    pl.t_full = 0;
+  } else if (pl.tiles > sms && g_tc_tuning.split_k == 0) {
+    // several waves: split only the partial LAST wave so that it keeps every SM busy (a quarter-full last wave of
+    // whole tiles costs a whole tile time)
+    const int tail = pl.tiles % sms;
+    if (tail != 0 && tail * 2 <= sms) {
+      ks = sms / tail;
+      while (ks > 1 && kblocks / ks < 8) --ks;
+      if (ks > 8) ks = 8;
+      if (ks > 1) pl.t_full = pl.tiles - tail;
+    }
   }
   if (ks > kblocks) ks = kblocks;
   if (ks > 32) ks = 32;
+  if (ks <= 1) pl.t_full = pl.tiles;
+  pl.t_tail = pl.tiles - pl.t_full;
   pl.kb_per_split = (kblocks + ks - 1) / ks;
-  pl.split_k = (kblocks + pl.kb_per_split - 1) / pl.kb_per_split;
+  pl.splits = pl.t_tail > 0 ? (kblocks + pl.kb_per_split - 1) / pl.kb_per_split : 1;
+  if (pl.splits <= 1) {
+    pl.splits = 1;
+    pl.t_full = pl.tiles;
+    pl.t_tail = 0;
+  }
   return pl;
 }
 
@@ -781,7 +836,7 @@ bool tc_supported(const Problem& p, int bits) {
 
 size_t tc_workspace_bytes(int64_t M, int64_t K, int64_t N) {
   const TcPlan pl = tc_plan(int(M), int(K), int(N));
-  return pl.split_k > 1 ? size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.split_k) * M * N * sizeof(float) : 0;
+  return pl.splits > 1 ? size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.splits) * pl.t_tail * pl.m_tile * 128 * sizeof(float) : 0;
 }
 
 template <class A, int BITS, int MT, bool TS, int ZK>
@@ -878,9 +933,10 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
   // Optional (cb200_set_tc_cluster): CTAs with neighbouring n tiles and the same m tile share the x tile -- each fetches
   // 1/cluster of it and multicasts.  Measured neutral (2) to slightly slower (4) on every prefill shape: the x traffic
   // from L2 is not what limits this kernel, so the default is no cluster.
-  const int n_tiles = (p.N + 127) / 128;
+  const int n_tiles = pl.n_tiles;
   int cluster = g_tc_cluster > 0 ? g_tc_cluster : 1;
-  while (cluster > 1 && (n_tiles % cluster != 0 || mt / cluster < 8)) cluster /= 2;
+  // (clusters are runs of `cluster` consecutive work items: they must be n-neighbours of one m tile in both item ranges)
+  while (cluster > 1 && (n_tiles % cluster != 0 || mt / cluster < 8 || pl.t_full % cluster != 0 || pl.t_tail % cluster != 0)) cluster /= 2;
 
   CUtensorMap mx, mw;
   if (int rc = make_tmaps(enc, p, bits, act_dtype, mt / cluster, mx, mw)) return rc;
@@ -888,21 +944,25 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
   TcParams prm;
   prm.p = p;
   prm.kblocks_total = p.K / 64;
+  prm.n_tiles = pl.n_tiles;
+  prm.t_full = pl.t_full;
+  prm.t_tail = pl.t_tail;
+  prm.splits = pl.splits;
   prm.kb_per_split = pl.kb_per_split;
   prm.ws_partial = nullptr;
   prm.cluster = cluster;
 #ifdef CB200_TC_TRACE
   prm.trace = g_tc_trace;
 #endif
-  if (pl.split_k > 1) {
-    const size_t need = size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.split_k) * p.M * p.N * sizeof(float);
+  if (pl.splits > 1) {
+    const size_t need = size_t(CB200_WORKSPACE_COUNTER_BYTES) + size_t(pl.splits) * pl.t_tail * mt * 128 * sizeof(float);
     if (!ws || ws_bytes < need) {
-      set_error("tcgen05 split-K=%d needs %zu workspace bytes, got %zu", pl.split_k, need, ws_bytes);
+      set_error("tcgen05 split-K=%d over %d tiles needs %zu workspace bytes, got %zu", pl.splits, pl.t_tail, need, ws_bytes);
       return CB200_ERR_WORKSPACE;
     }
     prm.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES);
   }
-  dim3 grid((p.N + 127) / 128, (p.M + mt - 1) / mt, pl.split_k);
+  dim3 grid(pl.t_full + pl.t_tail * pl.splits, 1, 1);
 
   const bool ts = variant != CB200_TC_SS;
   int rc;
@@ -917,11 +977,11 @@ int launch_tc(const Problem& p, int bits, int act_dtype, int variant, void* ws, 
   }
   if (rc) return rc;
   if (launches) ++*launches;
-  if (pl.split_k > 1) {
-    const int64_t total4 = int64_t(p.M) * p.N / 4;  // N % 64 == 0
+  if (pl.splits > 1) {
+    const int64_t total4 = int64_t(pl.t_tail) * mt * 32;
     int blocks = int((total4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(prm.ws_partial, p.out, total4, pl.split_k, p.out_dtype);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(prm.ws_partial, p, mt, pl.n_tiles, pl.t_full, pl.t_tail, pl.splits);
     CB200_CUDA_CHECK(cudaGetLastError());
     if (launches) ++*launches;
   }

@@ -424,3 +424,11 @@ def test_tc2_matches_tc_ts_bit_for_bit_and_repeats():
     assert torch.equal(a, b)
     # same K order, one accumulator per tile in both kernels (TC_TS splits K over two accumulators only for m_tile <= 128)
     assert torch.equal(a, ref)
+
+
+@pytest.mark.parametrize("m,k,n,dtype,wname", [(512, 1024, 10240, torch.float16, "uint4"), (300, 2048, 10176, torch.bfloat16, "uint4b8"),
+                                               (2048, 512, 2560, torch.float16, "uint8")])
+def test_tc_split_of_the_partial_last_wave(m, k, n, dtype, wname):
+    """More tiles than SMs with a small remainder: the last wave's tiles are split along K (work items after the whole tiles)."""
+    _run_case(m, k, n, wname, 128, dtype, wname != "uint4b8", variant=_lib.TC_TS)
+    _run_case(m, k, n, wname, 128, dtype, wname != "uint4b8", variant=_lib.TC_SS)
