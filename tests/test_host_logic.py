@@ -141,3 +141,16 @@ def test_packaged_quantiser_equals_oracle(dtype, wname, zp, g):
         assert (u is None and v is None) or torch.equal(u, v)
     assert torch.equal(quant_utils.pack_rows(a[1], st.size_bits), oracle.pack_rows(b[1], st.size_bits))
     assert (st.size_bits, st.bias) == (oracle.WEIGHT_TYPES[wname].bits, oracle.WEIGHT_TYPES[wname].bias)
+
+
+def test_workspace_sizes_stay_small_for_the_llama_shapes():
+    """Scratch is split-K partials only: tile-local for the tcgen05 path (never an [M, N] plane per split), a few fp32 rows
+    per column block for the decode path.  Pure host arithmetic in the library -- runs without a GPU."""
+    lib = _lib.load()
+    mib = 1 << 20
+    for m, k, n in [(1, 4096, 4096), (1, 4096, 28672), (8, 14336, 4096), (16, 4096, 28672), (64, 4096, 4096),
+                    (512, 4096, 28672), (2048, 4096, 14336), (4096, 4096, 14336), (4096, 8192, 4096), (4096, 8192, 28672)]:
+        for bits in (4, 8):
+            need = lib.cb200_mpgemm_workspace_bytes(m, k, n, bits, _lib.AUTO)
+            assert need == 0 or need >= _lib.WORKSPACE_COUNTER_BYTES
+            assert need < 96 * mib, (m, k, n, bits, need)
