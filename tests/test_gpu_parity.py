@@ -432,3 +432,18 @@ def test_tc_split_of_the_partial_last_wave(m, k, n, dtype, wname):
     """More tiles than SMs with a small remainder: the last wave's tiles are split along K (work items after the whole tiles)."""
     _run_case(m, k, n, wname, 128, dtype, wname != "uint4b8", variant=_lib.TC_TS)
     _run_case(m, k, n, wname, 128, dtype, wname != "uint4b8", variant=_lib.TC_SS)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# smallest / odd shapes of the domain: one K block, column-block counts that are not multiples of 4, ragged M
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,k,n", [(1, 64, 64), (3, 128, 192), (8, 192, 64), (5, 320, 448), (16, 64, 64), (17, 64, 64), (33, 128, 320),
+                                   (130, 192, 192), (257, 64, 128), (300, 448, 64)])
+@pytest.mark.parametrize("dtype,wname,zp,g", [(torch.float16, "uint4", True, 64), (torch.bfloat16, "uint4b8", False, -1),
+                                              (torch.float16, "uint8b128", False, 64), (torch.bfloat16, "uint8", True, -1)])
+def test_smallest_and_odd_shapes(m, k, n, dtype, wname, zp, g):
+    _run_case(m, k, n, wname, g, dtype, zp)
+    if m <= 16:
+        _run_case(m, k, n, wname, g, dtype, zp, variant=_lib.DECODE_MMA)
+    _run_case(m, k, n, wname, g, dtype, zp, variant=_lib.TC_TS)
+    _run_case(m, k, n, wname, g, dtype, zp, variant=_lib.TC2_TS)
