@@ -92,6 +92,7 @@ struct DecodeGeom {
   int warp_smem;      // per-warp smem bytes (group rows + mbarrier)
   int cta_x_bytes;    // per-CTA smem bytes of the shared x slab (the 4 warps of a CTA work on the same K slab)
   int cb_padded;      // column blocks rounded up to a multiple of 4 (whole CTAs per slab; padding warps only sync)
+  int cta_aux_bytes;  // per-CTA smem after the x slab: chunk sums [m_rows][slab_k / 8] + group sums [ngroups][8] (fp32)
 };
 
 template <class A>
@@ -128,7 +129,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
 
 // A: activation type, BITS: 4|8, MT: 8-row m tiles (1: M<=8, 2: M<=16), U: steps per batch (group boundaries fall on
 // batch boundaries), ZK: cb200_zp_kind (compile time), FUSED: feed magic-number operands to the MMA (see above).
-template <class A, int BITS, int MT, int U, int ZK, bool FUSED>
+template <class A, int BITS, int MT, int U, int ZK, bool FUSED, bool XSUM = false>
 __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
     decode_kernel(const Problem p, const DecodeGeom geo, float* __restrict__ ws_partial, unsigned int* __restrict__ ws_counter) {
   constexpr int PF = 32 / BITS;     // k per packed word
@@ -184,9 +185,10 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
   const uint32_t xs_base = smem0;
-  const uint32_t meta_base = smem0 + geo.cta_x_bytes + (threadIdx.x >> 5) * geo.warp_smem;
+  const uint32_t aux_base = smem0 + geo.cta_x_bytes;                       // chunk sums, then group sums (XS path)
+  const uint32_t meta_base = aux_base + geo.cta_aux_bytes + (threadIdx.x >> 5) * geo.warp_smem;
   const uint32_t bar = meta_base + geo.ngroups * geo.meta_row_bytes;
-  const uint32_t xbar = smem0 + geo.cta_x_bytes + 4 * geo.warp_smem;
+  const uint32_t xbar = aux_base + geo.cta_aux_bytes + 4 * geo.warp_smem;
   const int g0 = b0 / bpg;  // a slab either covers whole groups or lies inside one group
   const int slab_k = nsteps * 4 * PF;
   constexpr uint32_t ZROW = ZK == CB200_ZP_I32 ? 128u : ZK == CB200_ZP_U8 ? 32u : ZK == CB200_ZP_ACT ? 64u : 0u;  // 32 columns
@@ -250,6 +252,68 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   }
 
   DEC_STAMP(6);
+  constexpr bool HALF = std::is_same<A, __half>::value;
+  constexpr bool PRESCALE = FUSED && HALF && BITS == 4;  // nibbles at bits 4-7 arrive as 16 q: their activations get x 1/16
+  // XS: the group sums X[g][m] = sum_k x[m,k] are computed ONCE per CTA from the staged slab (deterministic two-pass
+  // reduction below) instead of by an all-ones MMA per operand pair in every warp, and (int4) the slab is rewritten in the
+  // operand order the main loop wants -- pairs (k0,k4),(k1,k5),(k2,k6),(k3,k7), the x16 partners pre-scaled by 1/16 -- so a
+  // step reads its activations with one ld.shared.v4 and nothing else.  4 instead of 6 MMAs per step.
+  // (XSUM is chosen by the host for M <= 2 and long slabs: the CTA-wide prologue costs two barriers and a pass over x,
+  //  measured +0.5 us on the 2-batch slabs of the 4096 x 4096 layer and slower for M = 8, -1.2 us on the 58.7 MB layer)
+  constexpr bool XS = FUSED && MT == 1 && XSUM;
+  const uint32_t xsum_base = aux_base + uint32_t(M) * uint32_t(slab_k / 8) * 4u;  // [ngroups][8] fp32 after the chunk sums
+  if constexpr (XS) {
+    const int nchunks = slab_k / 8;  // 16-byte chunks (8 activations) per row
+    // threads taking part: the CTA's padding warps (column block >= C, always the last ones) have already left
+    const int nthr = 32 * min(4, C - (cb - int(threadIdx.x >> 5)));
+    auto sum2 = [](uint32_t v) -> float {
+      if constexpr (HALF) {
+        const float2 f = __half22float2(bits_h2(v));
+        return f.x + f.y;
+      } else {
+        const float2 f = __bfloat1622float2(bits_b2(v));
+        return f.x + f.y;
+      }
+    };
+    for (int i = threadIdx.x; i < geo.ngroups * 8; i += nthr) {  // rows >= M stay zero (their outputs are never stored)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum_base + 4u * i), "f"(0.f) : "memory");
+    }
+    for (int m = 0; m < M; ++m) {
+      for (int cc = threadIdx.x; cc < nchunks; cc += nthr) {
+        const uint32_t addr = xs_base + m * geo.x_row_bytes + cc * 16;
+        const uint4 v = lds128(addr);
+        const float cs = (sum2(v.x) + sum2(v.y)) + (sum2(v.z) + sum2(v.w));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aux_base + 4u * (m * nchunks + cc)), "f"(cs) : "memory");
+        if constexpr (BITS == 4) {
+          uint32_t o0 = __byte_perm(v.x, v.z, 0x5410);  // (k0,k4)
+          uint32_t o1 = __byte_perm(v.x, v.z, 0x7632);  // (k1,k5)
+          uint32_t o2 = __byte_perm(v.y, v.w, 0x5410);  // (k2,k6)
+          uint32_t o3 = __byte_perm(v.y, v.w, 0x7632);  // (k3,k7)
+          if constexpr (PRESCALE) {
+            o1 = ActOps<A>::mul(o1, 0x2C002C00u);
+            o3 = ActOps<A>::mul(o3, 0x2C002C00u);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+        }
+      }
+    }
+    __syncthreads();
+    // second pass: one (row, group) per thread, chunk sums added in order
+    const int cpg = geo.ngroups > 1 ? (bpg * U * 4 * PF) / 8 : nchunks;  // chunks per group inside this slab
+    for (int t = threadIdx.x; t < M * geo.ngroups; t += nthr) {
+      const int m = t / geo.ngroups, gi = t - m * geo.ngroups;
+      float acc_x = 0.f;
+      const uint32_t src = aux_base + 4u * (m * nchunks + gi * cpg);
+      for (int c = 0; c < cpg; ++c) {
+        float f;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(src + 4u * c));
+        acc_x += f;
+      }
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum_base + 4u * (gi * 8 + m)), "f"(acc_x) : "memory");
+    }
+    __syncthreads();
+  }
+  uint32_t xsum_cur = xsum_base;  // XS: group sums of the current group
   // ---- consume-side state ---------------------------------------------------------------------------------------------------
   float zscalar = 0.f;
   A zfscalar = A(0.f);
@@ -261,8 +325,6 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   int batches_left = bpg - (b0 % bpg);  // batches until the current group ends
   bool refresh = true;
   const float fbias = float(p.bias);
-  constexpr bool HALF = std::is_same<A, __half>::value;
-  constexpr bool PRESCALE = FUSED && HALF && BITS == 4;  // odd nibbles are 1024 + 16 q: their activations get x 1/16
   constexpr float MAGIC = HALF ? 0.f : 128.f;           // bf16 operands are 128 + q; fp16 operands are q * 2^-24
   constexpr float OPSCALE = HALF ? 16777216.f : 1.f;    // 2^24 undoes the subnormal scaling
   constexpr uint32_t ONE2 = HALF ? 0x3C003C00u : 0x3F803F80u;      // (1.0, 1.0)
@@ -286,7 +348,14 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
 
   auto close_group = [&]() {  // FUSED: acc += sa[n] * G[m,n] + sb[n] * X[m]
     // C fragment: c0,c1 <- weight column 2t (m = 2tig, 2tig+1); c2,c3 <- weight column 2t+1 of this lane;
-    // the ones-MMA leaves X[2tig], X[2tig+1] in c0,c1 (and again in c2,c3)
+    // the ones-MMA leaves X[2tig], X[2tig+1] in c0,c1 (and again in c2,c3); the XS path reads them from shared memory
+    if constexpr (XS) {
+      float x0, x1;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(xsum_cur + 8u * tig));
+      accx[0][0] = accx[0][2] = x0;
+      accx[0][1] = accx[0][3] = x1;
+      xsum_cur += 32u;
+    }
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -349,10 +418,14 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         if constexpr (BITS == 4) {
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
           if (m_ok[mt]) v = lds128(lane_x[mt] + (step + u) * (4 * PF * 2));
-          xb[mt][0] = __byte_perm(v.x, v.z, 0x5410);  // (k0,k4)
-          xb[mt][1] = __byte_perm(v.x, v.z, 0x7632);  // (k1,k5)
-          xb[mt][2] = __byte_perm(v.y, v.w, 0x5410);  // (k2,k6)
-          xb[mt][3] = __byte_perm(v.y, v.w, 0x7632);  // (k3,k7)
+          if constexpr (XS) {  // the slab was rewritten in operand order (and pre-scaled) by the CTA prologue
+            xb[mt][0] = v.x; xb[mt][1] = v.y; xb[mt][2] = v.z; xb[mt][3] = v.w;
+          } else {
+            xb[mt][0] = __byte_perm(v.x, v.z, 0x5410);  // (k0,k4)
+            xb[mt][1] = __byte_perm(v.x, v.z, 0x7632);  // (k1,k5)
+            xb[mt][2] = __byte_perm(v.y, v.w, 0x5410);  // (k2,k6)
+            xb[mt][3] = __byte_perm(v.y, v.w, 0x7632);  // (k3,k7)
+          }
         } else {
           uint2 v = make_uint2(0u, 0u);
           if (m_ok[mt]) v = lds64(lane_x[mt] + (step + u) * (4 * PF * 2));
@@ -383,7 +456,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          if constexpr (PRESCALE) {  // activations that meet the x16 operands: x * 1/16
+          if constexpr (PRESCALE && !XS) {  // activations that meet the x16 operands: x * 1/16
             xb[mt][1] = ActOps<A>::mul(xb[mt][1], 0x2C002C00u);
             xb[mt][3] = ActOps<A>::mul(xb[mt][3], 0x2C002C00u);
           }
@@ -401,10 +474,12 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
               }
             }
             // X[m] += sum_k x[m,k] over this operand pair's 16 k (all 16 rows of the result are equal)
-            if (fresh && h == 0) {
-              mma16816<A>(accx[mt], zero4, ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
-            } else {
-              mma16816<A>(accx[mt], accx[mt], ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
+            if constexpr (!XS) {
+              if (fresh && h == 0) {
+                mma16816<A>(accx[mt], zero4, ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
+              } else {
+                mma16816<A>(accx[mt], accx[mt], ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
+              }
             }
           }
         }
@@ -510,7 +585,7 @@ struct DecodePlan {
   int bpg;             // batches per scale group
   int splits, units_per_warp, col_blocks, total_warps;
   int ctas_per_sm;
-  int x_row_bytes, meta_row_bytes, ngroups, warp_smem, max_units, cta_x_bytes, cta_smem, cb_padded;
+  int x_row_bytes, meta_row_bytes, ngroups, warp_smem, max_units, cta_x_bytes, cta_aux_bytes, cta_smem, cb_padded;
   bool fused;
 };
 
@@ -536,7 +611,12 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
     return ((ng * (64 + zrow) + 8 + 127) / 128) * 128;
   };
   auto cta_x_for = [&](int per) { return ((mrows * (per * pl.u * step_k * 2 + 64) + 127) / 128) * 128; };
-  auto cta_smem_for = [&](int per) { return cta_x_for(per) + 4 * warp_smem_for(per) + 16; };
+  // chunk sums [mrows][slab_k / 8] + group sums [ngroups][8], fp32 (used by the fused path for M <= 8)
+  auto cta_aux_for = [&](int per) {
+    const int ng = (per + pl.bpg - 1) / pl.bpg;
+    return ((mrows * (per * pl.u * step_k / 8) * 4 + ng * 32 + 127) / 128) * 128;
+  };
+  auto cta_smem_for = [&](int per) { return cta_x_for(per) + cta_aux_for(per) + 4 * warp_smem_for(per) + 16; };
   // the CTA's staging budget bounds the slab: x rows (2 B per k per row) within ~24 KB (48 KB for the 16-row variant)
   {
     const int budget = mrows > 8 ? 48 * 1024 : 24 * 1024;
@@ -578,7 +658,10 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
   pl.ngroups = (pl.units_per_warp + pl.bpg - 1) / pl.bpg;
   pl.warp_smem = warp_smem_for(pl.units_per_warp);
   pl.cta_x_bytes = cta_x_for(pl.units_per_warp);
-  pl.cta_smem = cta_smem_for(pl.units_per_warp);
+  // group sums of x once per CTA (4 instead of 6 MMAs per step): pays for M <= 2 on long slabs only (measured)
+  const bool xsum = pl.fused && mrows <= 2 && pl.units_per_warp >= 8 ;
+  pl.cta_aux_bytes = xsum ? cta_aux_for(pl.units_per_warp) : 0;
+  pl.cta_smem = cta_smem_for(pl.units_per_warp) - (xsum ? 0 : cta_aux_for(pl.units_per_warp));
   return pl;
 }
 
@@ -606,6 +689,9 @@ static int launch_fused(bool fused, const Problem& p, const DecodeGeom& geo, int
   // bf16 x int8: 128 + q does not fit a bf16 significand, so there is no magic-number operand -> per-weight dequant
   if (fused && !(std::is_same<A, __nv_bfloat16>::value && BITS == 8)) {
     kern = decode_kernel<A, BITS, MT, U, ZK, true>;
+    if constexpr (MT == 1) {
+      if (geo.cta_aux_bytes > 0) kern = decode_kernel<A, BITS, MT, U, ZK, true, true>;  // group sums of x once per CTA
+    }
   } else {
     kern = decode_kernel<A, BITS, MT, U, ZK, false>;
   }
@@ -688,6 +774,7 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     geo.warp_smem = pl.warp_smem;
     geo.cta_x_bytes = pl.cta_x_bytes;
     geo.cb_padded = pl.cb_padded;
+    geo.cta_aux_bytes = pl.cta_aux_bytes;
     const int blocks = (pl.total_warps + 3) / 4;
     float* wsp = ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + CB200_WORKSPACE_COUNTER_BYTES) : nullptr;
     unsigned* wsc = reinterpret_cast<unsigned*>(ws);

@@ -447,3 +447,20 @@ def test_smallest_and_odd_shapes(m, k, n, dtype, wname, zp, g):
         _run_case(m, k, n, wname, g, dtype, zp, variant=_lib.DECODE_MMA)
     _run_case(m, k, n, wname, g, dtype, zp, variant=_lib.TC_TS)
     _run_case(m, k, n, wname, g, dtype, zp, variant=_lib.TC2_TS)
+
+
+@pytest.mark.parametrize("m", [1, 2])
+@pytest.mark.parametrize("dtype,wname,zp", [(torch.float16, "uint4", True), (torch.float16, "uint8", True), (torch.bfloat16, "uint4b8", False),
+                                            (torch.float16, "uint8b128", False)])
+@pytest.mark.parametrize("g", [64, 128, 256, -1])
+def test_decode_group_sums_prologue(m, dtype, wname, zp, g):
+    """M <= 2 on long slabs: the CTA computes the group sums of x once (and rewrites the slab in operand order) instead of
+    an all-ones MMA per operand pair.  One split forces 16..32 batches per warp, i.e. that path."""
+    lib = _lib.load()
+    try:
+        lib.cb200_set_decode_tuning(0, 0, 1, 0)
+        _run_case(m, 2048, 320, wname, g, dtype, zp, variant=_lib.DECODE_MMA)
+        lib.cb200_set_decode_tuning(0, 0, 2, 0)
+        _run_case(m, 4096, 192, wname, g, dtype, zp, variant=_lib.DECODE_MMA, zp_as=torch.uint8 if zp else None)
+    finally:
+        lib.cb200_set_decode_tuning(0, 0, 0, 0)
