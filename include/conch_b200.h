@@ -118,7 +118,11 @@ CB200_API int cb200_dequantize(const void* w_q_packed, const void* w_s, const vo
                      int weight_size_bits, int weight_bias, int64_t group_size,
                      int act_dtype, int zp_kind, int zp_is_scalar, void* stream);
 
-/* Debug/tuning knobs: override the decode kernel's tiling (0 = heuristic).  Process-global, not thread-safe. */
+/* Debug/tuning knobs of the decode kernel (0 = heuristic).  Process-global, not thread-safe.
+ *   warps_n   1: dequantise every weight before the MMA (W bits equal the reference's w_ref); 0/2: fused operands (default)
+ *   warps_k   CTAs per SM assumed resident when the split count is chosen
+ *   split_k   forced number of K slabs per 32-column block (rounded to a legal divisor)
+ *   vec_words unused */
 CB200_API void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_words);
 /* Debug/tuning knobs for the tcgen05 family: m_tile (MMA N: 16..256, 0 = heuristic), split_k (0 = heuristic). */
 CB200_API void cb200_set_tc_tuning(int m_tile, int split_k);
