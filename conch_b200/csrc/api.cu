@@ -1,10 +1,12 @@
 // extern "C" entry points of libconch_b200.so (declared in include/conch_b200.h) + regime dispatch.
 // Replaces the reference's launcher + dispatch (conch/kernels/quantization/gemm.py:482-545 and the platform
 // switch in conch/platforms/__init__.py:14-19): there is exactly one backend, sm_100a.
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
 #include "common.cuh"
+#include "host_util.cuh"
 
 namespace cb200 {
 
@@ -19,20 +21,50 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int check_device() {
-  static std::once_flag once;
-  static int status = 0;
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-      status = CB200_ERR_DEVICE;
-      return;
+// ---- per-device facts (one process may drive several GPUs: nothing here is cached per process) ---------------------
+const DeviceInfo* current_device_info() {
+  static DeviceInfo table[CB200_MAX_DEVICES];
+  static std::atomic<int> state[CB200_MAX_DEVICES];  // 0 unknown, 1 valid
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= CB200_MAX_DEVICES) return nullptr;
+  if (state[dev].load(std::memory_order_acquire) != 1) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (state[dev].load(std::memory_order_relaxed) != 1) {
+      DeviceInfo di;
+      di.index = dev;
+      if (cudaDeviceGetAttribute(&di.sm_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+          cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        return nullptr;
+      }
+      table[dev] = di;
+      state[dev].store(1, std::memory_order_release);
     }
-    if (prop.major != 10) status = CB200_ERR_DEVICE;
+  }
+  return &table[dev];
+}
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {  // a driver entry point, not a device property: process-wide is correct
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
   });
-  if (status != 0) set_error("libconch_b200 requires an sm_100 (B200) device; there is no fallback path");
-  return status;
+  return fn;
+}
+
+static int check_device() {
+  const DeviceInfo* di = current_device_info();
+  if (!di || di->sm_major != 10) {
+    set_error("libconch_b200 requires an sm_100 (B200) device; there is no fallback path");
+    return CB200_ERR_DEVICE;
+  }
+  return 0;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -106,13 +138,20 @@ void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_word
 void cb200_set_tc_tuning(int m_tile, int split_k) { g_tc_tuning = {m_tile, split_k}; }
 void cb200_set_tc_cluster(int ctas) { g_tc_cluster = (ctas == 1 || ctas == 2 || ctas == 4) ? ctas : 0; }
 void cb200_set_pdl(int enable) { g_decode_pdl = enable ? 1 : 0; }
+void cb200_set_stream_tuning(int ring_kb, int ctas) { g_stream_tuning = {ring_kb, ctas, g_stream_tuning.dbg}; }
+void cb200_debug_set_stream_switches(int switches) { g_stream_tuning.dbg = switches; }
+void cb200_debug_set_stream_trace(void* device_buffer) { g_stream_trace = reinterpret_cast<long long*>(device_buffer); }
 
 size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_size_bits, int variant) {
   (void)variant;
   const int bits = weight_size_bits == 8 ? 8 : 4;
   const size_t a = decode_workspace_bytes(M, K, N, bits);
   const size_t b = tc_workspace_bytes(M, K, N);
-  return a > b ? a : b;
+  const size_t c = stream_workspace_bytes(M, K, N, bits);
+  const size_t d = tcs_workspace_bytes(M, K, N, bits);
+  size_t need = a > b ? a : b;
+  need = c > need ? c : need;
+  return d > need ? d : need;
 }
 
 int cb200_dequantize(const void* w_q_packed, const void* w_s, const void* w_zp, void* w_out, int64_t K, int64_t N,
@@ -192,19 +231,33 @@ int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, co
 
   int chosen = variant;
   if (chosen == CB200_AUTO) {
-    // regime split: HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x), tcgen05 pipeline above (measured at
-    // M = 16: 10.7 vs 18.4 us on the 4096 x 4096 layer, 37 vs 61 us on 4096 x 28672 -- profiles/r01_midm_probe.log)
+    // regime split by MEASUREMENT (profiles/r02_decode_variants.log): HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile
+    // of x) on the register-window kernel; tcgen05 pipeline above.  The two streaming kernels (CB200_DECODE_STREAM,
+    // CB200_DECODE_TCS) are parity-tested opt-in variants: on a B200 their fine-grained producer / consumer handshakes cost
+    // more than the cross-kernel overlap they buy.
     const bool decode = M <= 8;
     chosen = (decode || !tc_supported(p, weight_size_bits)) ? CB200_DECODE_MMA : CB200_TC_TS;
   }
-  if (num_peers > 0 && chosen != CB200_DECODE_MMA) {
-    // the fused push lives in the decode kernel's (tiny) epilogue; big outputs are bandwidth-bound: all-gather them
-    set_error("cb200_mpgemm_push: only the decode kernel (M <= 16) stores to peers; use an all-gather for M=%lld", (long long)M);
+  if (num_peers > 0 && chosen != CB200_DECODE_MMA && chosen != CB200_DECODE_STREAM && chosen != CB200_DECODE_TCS) {
+    // the fused push lives in the decode kernels' (tiny) epilogue; big outputs are bandwidth-bound: all-gather them
+    set_error("cb200_mpgemm_push: only the decode kernels (M <= 16) store to peers; use an all-gather for M=%lld", (long long)M);
     return CB200_ERR_UNSUPPORTED;
   }
   int launches = 0;
   if (chosen == CB200_DECODE_MMA) {
     rc = launch_decode(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
+  } else if (chosen == CB200_DECODE_STREAM) {
+    if (!stream_supported(p, weight_size_bits, act_dtype)) {
+      set_error("the streaming decode kernel does not support this problem (bf16 x int8: use CB200_DECODE_MMA)");
+      return CB200_ERR_UNSUPPORTED;
+    }
+    rc = launch_stream(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
+  } else if (chosen == CB200_DECODE_TCS) {
+    if (!tcs_supported(p, weight_size_bits, act_dtype)) {
+      set_error("the tcgen05 streaming decode kernel does not support this problem (bf16 x int8, or int4 with group_size %% 128 != 0)");
+      return CB200_ERR_UNSUPPORTED;
+    }
+    rc = launch_tcs(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
   } else if (chosen == CB200_TC_SS || chosen == CB200_TC_TS || chosen == CB200_TC2_TS) {
     if (!tc_supported(p, weight_size_bits)) {
       set_error("tcgen05 variant %d does not support this problem", chosen);

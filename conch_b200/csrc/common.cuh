@@ -53,6 +53,20 @@ int launch_tc2(const Problem& p, int bits, int act_dtype, cudaStream_t stream, i
 size_t tc_workspace_bytes(int64_t M, int64_t K, int64_t N);
 bool tc_supported(const Problem& p, int bits);
 
+int launch_stream(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+size_t stream_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
+bool stream_supported(const Problem& p, int bits, int act_dtype);
+int launch_tcs(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+size_t tcs_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
+bool tcs_supported(const Problem& p, int bits, int act_dtype);
+struct StreamTuning {
+  int ring_kb;   // shared memory the ring may use per CTA, in KiB (0 = heuristic)
+  int ctas;      // CTAs launched (0 = one per SM)
+  int dbg;       // debug switches, see StreamGeom::dbg (results are wrong when set: timing experiments only)
+};
+extern StreamTuning g_stream_tuning;
+extern long long* g_stream_trace;  // device buffer the next stream_kernel launches stamp (nullptr = off)
+
 struct DecodeTuning {
   int warps_n, warps_k, split_k, vec_words;
 };
@@ -81,6 +95,30 @@ template <class T>
 __device__ __forceinline__ void store_out_all(const Problem& p, size_t idx, float v) {
   store_out<T>(p.out, p.out_dtype, idx, v);
   for (int i = 0; i < p.n_peers; ++i) store_out<T>(p.peer_out[i], p.out_dtype, idx, v);
+}
+
+// four consecutive outputs (idx % 4 == 0) as ONE vector store per destination: 8 bytes for fp16 / bf16, 16 for fp32 --
+// the shape the multi-GPU push wants (one NVLink write per peer instead of four 2-byte ones)
+__device__ __forceinline__ void store_out4(void* out, int out_dtype, size_t idx, float4 v) {
+  if (out_dtype == CB200_F16) {
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + idx) = pk;
+  } else if (out_dtype == CB200_BF16) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + idx) = pk;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + idx) = v;
+  }
+}
+__device__ __forceinline__ void store_out4_all(const Problem& p, size_t idx, float4 v) {
+  store_out4(p.out, p.out_dtype, idx, v);
+  for (int i = 0; i < p.n_peers; ++i) store_out4(p.peer_out[i], p.out_dtype, idx, v);
 }
 
 // streaming (read-once) global loads: bypass L1 allocation

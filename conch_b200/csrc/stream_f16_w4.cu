@@ -1,0 +1,6 @@
+// streaming decode kernel instantiations: __half activations, 4-bit weights (see stream_impl.cuh / stream_kernel.cu)
+#include "stream_impl.cuh"
+
+namespace cb200 {
+CB200_STREAM_ENTRY(launch_stream_f16_w4) { return launch_stream_typed<__half, 4>(mw, mx, p, geo, ctas, smem, wsp, wsc, stream); }
+}  // namespace cb200

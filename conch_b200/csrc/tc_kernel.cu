@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "dequant.cuh"
+#include "host_util.cuh"
 #include "tc_ptx.cuh"
 
 namespace cb200 {
@@ -749,38 +750,14 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, Problem p, 
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-  });
-  return fn;
-}
-
 struct TcPlan {
   int m_tile, n_tiles, tiles;
   int t_full, t_tail, splits, kb_per_split;
 };
 
 static int tc_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
-      sms = 148;
-    }
-  }
-  return sms;
+  const DeviceInfo* di = current_device_info();
+  return di && di->sms > 0 ? di->sms : 148;
 }
 
 static TcPlan tc_plan(int M, int K, int N) {
@@ -843,11 +820,8 @@ template <class A, int BITS, int MT, bool TS, int ZK>
 static int launch_cfg(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& prm, dim3 grid, cudaStream_t stream) {
   using Cfg = TcCfg<MT, BITS, TS>;
   auto kern = tc_kernel<A, BITS, MT, TS, ZK>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    CB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  static unsigned long long attr_mask = 0;  // per instantiation, one bit per device
+  if (int rc = set_max_smem_once(kern, Cfg::SMEM_BYTES, attr_mask)) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kTcThreads);
@@ -1010,12 +984,7 @@ int launch_tc2(const Problem& p, int bits, int act_dtype, cudaStream_t stream, i
     set_error("cuTensorMapEncodeTiled driver entry point not available");
     return CB200_ERR_DEVICE;
   }
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    CB200_CUDA_CHECK(cudaGetDevice(&dev));
-    CB200_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = tc_sm_count();
   CUtensorMap mx, mw;
   if (int rc = make_tmaps(enc, p, bits, act_dtype, 128, mx, mw)) return rc;
   Tc2Params prm;

@@ -1,0 +1,6 @@
+// tcgen05 streaming decode kernel instantiations: __half activations, 8-bit weights (see tcs_impl.cuh / tcs_kernel.cu)
+#include "tcs_impl.cuh"
+
+namespace cb200 {
+CB200_TCS_ENTRY(launch_tcs_f16_w8) { return launch_tcs_typed<__half, 8>(mt, mw, mx, p, geo, ctas, smem, wsp, wsc, stream); }
+}  // namespace cb200

@@ -23,8 +23,11 @@ INDEX = golden_index()
 ALL_VARIANTS = [_lib.DECODE_MMA, _lib.TC_SS, _lib.TC_TS]
 
 
-def _variants_for(m: int) -> list[int]:
-    return ALL_VARIANTS
+def _variants_for(entry: dict) -> list[int]:
+    """Every kernel family that accepts the fixture (the streaming decode kernel has no bf16 x int8 operand format)."""
+    if entry["dtype"] == "bf16" and entry["bits"] == 8:
+        return ALL_VARIANTS
+    return ALL_VARIANTS + [_lib.DECODE_STREAM]
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -59,7 +62,7 @@ def test_gemm_vs_reference_fixture(entry):
     g = load_golden(entry)
     x, wq, ws, wzp = to_cuda(g["x"], g["w_q_packed"], g["w_s"], g["w_zp"])
     want = oracle.mixed_precision_gemm_ref(g["x"], g["w_q_packed"], g["w_s"], g["w_zp"], entry["bits"], entry["bias"], entry["group_size"])
-    for variant in _variants_for(x.shape[0]):
+    for variant in _variants_for(entry):
         out = mixed_precision_gemm(x, wq, ws, wzp, entry["bits"], entry["bias"], entry["group_size"], variant=variant)
         assert out.shape == (entry["m"], entry["n"]) and out.dtype == x.dtype
         assert_gemm_close(out, want, f"variant {variant}")

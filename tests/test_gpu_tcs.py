@@ -1,0 +1,229 @@
+"""GPU parity tests of the tcgen05 streaming decode kernel (CB200_DECODE_TCS, AUTO's choice for M <= 32), through the C ABI.
+
+Like the mma.sync streaming kernel it never forms the rounded W: nibbles become subnormal fp16 (or 128 + q bf16) tensor-core
+operands, scales and zero-points are applied per scale group in fp32 from the TMEM accumulator.  GEMM bar: the north_star
+tolerance (rtol = atol = 1e-2 vs the fp32-accumulated oracle); one-hot activations must reproduce the reference's
+dequantised weights BIT FOR BIT; chains under programmatic dependent launch must be bit-identical to serial execution.
+"""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+import mpgemm_oracle as oracle
+from conch_b200 import _lib, quant_utils
+from conch_b200.ops.quantization.gemm import mixed_precision_gemm
+from helpers import assert_gemm_close, bits, to_cuda
+from test_gpu_stream import _case
+
+pytestmark = pytest.mark.gpu
+TCS = _lib.DECODE_TCS
+FORMATS = [(torch.float16, "uint4"), (torch.float16, "uint4b8"), (torch.float16, "uint8"), (torch.float16, "uint8b128"),
+           (torch.bfloat16, "uint4"), (torch.bfloat16, "uint4b8")]  # fmt: skip
+FORMAT_IDS = ["f16-u4", "f16-u4b8", "f16-u8", "f16-u8b128", "bf16-u4", "bf16-u4b8"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded(built_lib):
+    lib = _lib.load()
+    assert torch.cuda.is_available() and torch.cuda.get_device_capability()[0] == 10
+    yield
+    lib.cb200_set_pdl(0)
+    lib.cb200_set_stream_tuning(0, 0)
+    with open("/proc/self/maps") as f:
+        assert "libconch_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("m", [1, 2, 4, 5, 8, 13, 16, 17, 24, 32])
+@pytest.mark.parametrize("dtype,wname", FORMATS, ids=FORMAT_IDS)
+def test_rows_and_formats(m, dtype, wname):
+    out, want, _ = _case(m, 1024, 512, wname, 128, dtype, True, variant=TCS)
+    assert_gemm_close(out, want, f"M={m} {wname} {dtype}")
+
+
+@pytest.mark.parametrize("g", [128, 256, 384, 512, -1])
+@pytest.mark.parametrize("zp", [True, False], ids=["zp", "sym"])
+@pytest.mark.parametrize("dtype,wname", [(torch.float16, "uint4"), (torch.bfloat16, "uint4b8"), (torch.float16, "uint8b128")],
+                         ids=["f16-u4", "bf16-u4b8", "f16-u8b128"])  # fmt: skip
+def test_group_sizes(g, zp, dtype, wname):
+    k = 1536 if g in (384, 512) else 1024
+    out, want, _ = _case(5, k, 256, wname, g, dtype, zp, variant=TCS)
+    assert_gemm_close(out, want, f"g={g}")
+
+
+def test_int8_group_of_one_stage_and_unsupported_int4_group():
+    out, want, _ = _case(3, 512, 256, "uint8", 64, torch.float16, True, variant=TCS)  # int8: a 64-k group is exactly one stage
+    assert_gemm_close(out, want)
+    p = oracle.make_problem(3, 512, 256, "uint4", 64, torch.float16, True, seed=0)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    with pytest.raises(NotImplementedError):
+        mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 64, variant=TCS)
+
+
+@pytest.mark.parametrize("n", [64, 192, 320, 1088])  # N % 128 == 64: the last 128-column block is half empty
+@pytest.mark.parametrize("m", [1, 11, 29])
+def test_ragged_last_column_block(n, m):
+    out, want, _ = _case(m, 512, n, "uint4", 128, torch.float16, True, variant=TCS)
+    assert_gemm_close(out, want, f"N={n}")
+
+
+@pytest.mark.parametrize("zp_as", [torch.uint8, torch.float16], ids=["zp_u8", "zp_f16"])
+@pytest.mark.parametrize("wname", ["uint4", "uint8"])
+def test_zero_point_dtypes(zp_as, wname):
+    out, want, _ = _case(3, 512, 256, wname, 128, torch.float16, True, zp_as=zp_as, variant=TCS)
+    assert_gemm_close(out, want)
+
+
+def test_scalar_zero_point_and_output_dtypes():
+    p = oracle.make_problem(4, 512, 256, "uint4", 128, torch.float16, False, seed=5)
+    zp = torch.tensor([[7]], dtype=torch.int32)
+    x, wq, ws, z = to_cuda(p.x, p.w_q_packed, p.w_s, zp)
+    out = mixed_precision_gemm(x, wq, ws, z, 4, 0, 128, variant=TCS)
+    assert_gemm_close(out, oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, zp, 4, 0, 128))
+    for od in (torch.float32, torch.bfloat16):
+        out, want, _ = _case(2, 512, 256, "uint4", 128, torch.float16, True, out_dtype=od, variant=TCS)
+        assert out.dtype == od
+        assert_gemm_close(out, want)
+
+
+@pytest.mark.parametrize("k,n", [(4096, 4096), (4096, 6144), (14336, 4096), (4096, 28672)], ids=["o", "qkv", "down", "gate_up"])
+@pytest.mark.parametrize("m", [1, 4, 16, 32])
+def test_llama3_8b_decode_shapes(k, n, m):
+    """BASELINE config 2: W4A16, int4 asymmetric (uint4 + zero-points), g=128, fp16, full size."""
+    out, want, _ = _case(m, k, n, "uint4", 128, torch.float16, True, variant=TCS)
+    assert_gemm_close(out, want, f"{m}x{k}x{n}")
+
+
+@pytest.mark.parametrize("wname,g,dtype", [("uint8", 128, torch.float16), ("uint8b128", 128, torch.float16),
+                                           ("uint4", -1, torch.bfloat16), ("uint4b8", -1, torch.bfloat16)])  # fmt: skip
+@pytest.mark.parametrize("m", [1, 16, 32])
+def test_config4_formats_at_llama_size(wname, g, dtype, m):
+    """BASELINE config 4 (W8A16, per-channel int4 with bf16) on the 4096 x 4096 projection."""
+    out, want, _ = _case(m, 4096, 4096, wname, g, dtype, wname in ("uint8", "uint4"), variant=TCS)
+    assert_gemm_close(out, want)
+
+
+def test_70b_ffn_shard_shape():
+    """BASELINE config 5, one rank's shard at 8 GPUs: K = 8192, N = 28672 / 8."""
+    out, want, _ = _case(1, 8192, 3584, "uint4", 128, torch.float16, True, variant=TCS)
+    assert_gemm_close(out, want)
+
+
+@pytest.mark.parametrize("dtype,wname,zp", [(torch.float16, "uint4", True), (torch.float16, "uint4b8", False),
+                                            (torch.float16, "uint8", True), (torch.bfloat16, "uint4", True)])  # fmt: skip
+def test_one_hot_rows_reproduce_the_reference_weights_bit_for_bit(dtype, wname, zp):
+    """x = e_k selects row k of W: the per-group fp32 correction s*q - s*zb is exact, so the single rounding to the output
+    dtype is the reference's (conch/kernels/quantization/gemm.py:205-216)."""
+    k_dim, n = 2048, 384
+    p = oracle.make_problem(1, k_dim, n, wname, 128, dtype, zp, seed=3)
+    rows = [0, 1, 7, 8, 127, 128, 129, 1000, 1033, 2047, 5, 640, 77, 1291, 255, 256, 3, 4, 2, 6, 9, 65, 66, 67, 68, 69, 70, 71, 1999, 1023, 1024, 1025]
+    x = torch.zeros((32, k_dim), dtype=dtype)
+    for i, r in enumerate(rows):
+        x[i, r] = 1.0
+    xd, wq, ws, wzp = to_cuda(x, p.w_q_packed, p.w_s, p.w_zp)
+    for m in (1, 8, 16, 32):
+        out = mixed_precision_gemm(xd[:m].contiguous(), wq, ws, wzp, p.wtype.bits, p.wtype.bias, 128, variant=TCS)
+        assert torch.equal(bits(out), bits(p.w_ref[rows[:m]])), f"M={m}"
+
+
+@pytest.mark.parametrize("scale", [2.0**-12, 2.0**-20, 1e-4, 1e-6])
+def test_small_magnitude_activations_keep_their_bits(scale):
+    out, want, _ = _case(4, 4096, 512, "uint4", 128, torch.float16, True, out_dtype=torch.float32, x_scale=scale, variant=TCS)
+    torch.testing.assert_close(out.cpu().float() / scale, want.float() / scale, rtol=1e-2, atol=1e-2)
+
+
+def test_reference_recipe_at_llama_k():
+    out, want, _ = _case(2, 14336, 256, "uint4", 128, torch.float16, True, recipe="reference", out_dtype=torch.float32, variant=TCS)
+    torch.testing.assert_close(out.cpu().float(), want.float(), rtol=1e-2, atol=1e-2)
+
+
+def test_more_than_32_rows_runs_in_passes():
+    out, want, _ = _case(70, 1024, 256, "uint4", 128, torch.float16, True, variant=TCS)
+    assert_gemm_close(out, want)
+    assert _lib.load().cb200_last_launch_count() == 3
+
+
+def test_batch_rows_equal_single_rows_bit_for_bit():
+    """Row m of an M-row call sees exactly the arithmetic of a 1-row call (same stages, same MMA k order, same X-sum tree, same
+    slot order in the split-K sum): the results must be IDENTICAL, not merely close."""
+    p = oracle.make_problem(16, 4096, 1024, "uint4", 128, torch.float16, True, seed=11)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    full = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=TCS)
+    for m in (0, 3, 7, 15):
+        one = mixed_precision_gemm(x[m : m + 1].contiguous(), wq, ws, wzp, 4, 0, 128, variant=TCS)
+        assert torch.equal(bits(one[0]), bits(full[m])), f"row {m}"
+
+
+@pytest.mark.parametrize("ring_kb,ctas", [(30, 0), (0, 7), (0, 148), (60, 33), (200, 0), (0, 296)])
+def test_ring_depth_and_grid_do_not_break_the_result(ring_kb, ctas):
+    lib = _lib.load()
+    try:
+        lib.cb200_set_stream_tuning(ring_kb, ctas)
+        for m, k, n, wname, dtype in ((1, 2048, 1024, "uint4", torch.float16), (9, 1024, 640, "uint8b128", torch.float16),
+                                      (3, 4096, 320, "uint4b8", torch.bfloat16), (20, 2048, 256, "uint4", torch.float16)):  # fmt: skip
+            out, want, _ = _case(m, k, n, wname, 128, dtype, True, variant=TCS)
+            assert_gemm_close(out, want, f"ring_kb={ring_kb} ctas={ctas}")
+    finally:
+        lib.cb200_set_stream_tuning(0, 0)
+
+
+def _chain(pdl: bool, graph: bool):
+    """A decode-token-like chain: GEMV i+1 consumes the output of GEMV i (so x is NOT static)."""
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    st = quant_utils.scalar_types.uint4
+    dims = [(1024, 1536), (1536, 1024), (1024, 4096), (4096, 1024)] * 6
+    layers = [quant_utils.random_packed_weights(k, n, st, 128, torch.float16, dev, seed=50 + i) for i, (k, n) in enumerate(dims)]
+    x0 = (torch.randn((2, 1024), device=dev) * 0.5).to(torch.float16)
+    acts = [x0] + [torch.empty((2, n), device=dev, dtype=torch.float16) for _, n in dims]
+
+    def run():
+        for i, (wq, ws, wzp) in enumerate(layers):
+            mixed_precision_gemm(acts[i], wq, ws, wzp, 4, 0, 128, out=acts[i + 1], variant=TCS)
+
+    lib.cb200_set_pdl(0)
+    run()
+    torch.cuda.synchronize()
+    want = [a.clone() for a in acts]
+    try:
+        lib.cb200_set_pdl(1 if pdl else 0)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            if graph:
+                run()
+                s.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    run()
+                for _ in range(5):
+                    for a in acts[1:]:
+                        a.zero_()
+                    g.replay()
+            else:
+                for _ in range(5):
+                    for a in acts[1:]:
+                        a.zero_()
+                    run()
+        torch.cuda.synchronize()
+    finally:
+        lib.cb200_set_pdl(0)
+    for i, (a, w) in enumerate(zip(acts, want)):
+        assert torch.equal(bits(a), bits(w)), f"activation {i} differs under pdl={pdl} graph={graph}"
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+@pytest.mark.parametrize("pdl", [False, True], ids=["plain", "pdl"])
+def test_dependent_chain_is_bit_identical_under_overlap(pdl, graph):
+    _chain(pdl, graph)
+
+
+def test_push_epilogue_writes_every_peer_buffer():
+    p = oracle.make_problem(3, 1024, 448, "uint4", 128, torch.float16, True, seed=2)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    peers = [torch.zeros((3, 448), device="cuda", dtype=torch.float16) for _ in range(7)]
+    out = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=TCS, peer_out_ptrs=[t.data_ptr() for t in peers])
+    torch.cuda.synchronize()
+    for t in peers:
+        assert torch.equal(bits(t), bits(out))
+    assert_gemm_close(out, oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, 4, 0, 128))
