@@ -17,8 +17,10 @@ step streams its weights from HBM).  A "step" is one such token.
   cpu_baseline / --impl reference
             the reference's PyTorch path (`torch.matmul(x, w_ref)`, tests/mixed_precision_gemm_test.py:70) restated by
             the oracle, on this box's host cores, on a bounded sample (one layer's four projections per step).
-Multi-GPU (N > 1): weak scaling -- every rank owns an equally sized column (N) shard of an N-times wider layer, runs
-the same per-GPU step and all-gathers the outputs of every GEMM over NCCL (the path's only exchange step).
+Multi-GPU (N > 1): the headline line is weak-scaled -- every rank owns an equally sized column (N) shard of an N-times wider
+layer, runs the same per-GPU step, and the outputs of every GEMV are gathered on every rank (fused into the kernel's epilogue).
+Next to it, `config5_70b_ffn` reports BASELINE config 5 -- the Llama-3-70B FFN (K=8192, N=28672) column-sharded over the N GPUs,
+STRONG scaling, at M=1 (fused gather) and M=4096 (NCCL all-gather overlapped with the next GEMM): compute / gather / end to end.
 """
 
 from __future__ import annotations
@@ -126,43 +128,66 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's PyTorch path restated by the oracle (the one place bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference(steps: int, warmup: int) -> dict:
+def cpu_reference(steps: int, warmup: int, layers_per_step: int = LAYERS, budget_s: float = 150.0) -> dict:
+    """The reference's PyTorch path on the host cores: `torch.matmul(x, w_ref)` with w_ref pre-dequantised offline exactly as
+    tests/mixed_precision_gemm_test.py:70 does, restated by the oracle.  One step = `layers_per_step` layers x 4 projections
+    (the GPU arm's step when layers_per_step == 32).  Two distinct layers' weights (872 MB of fp16, far beyond any host cache)
+    are cycled, so every GEMV streams its weights from DRAM like the GPU arm does."""
     import torch
 
     sys.path.insert(0, str(ROOT / "oracle"))
     import mpgemm_oracle as oracle
 
+    torch.set_num_threads(os.cpu_count() or 1)  # explicit: under torchrun OMP_NUM_THREADS defaults to 1
     threads = torch.get_num_threads()
     gen = torch.Generator().manual_seed(0)
-    layers = []
-    for name, k, n in PROJECTIONS:
-        packed = torch.randint(-(1 << 31), (1 << 31) - 1, (k // 8, n), generator=gen, dtype=torch.int64).to(torch.int32)
-        w_s = (0.004 + 0.004 * torch.rand((k // GROUP, n), generator=gen)).to(torch.float16)
-        w_zp = torch.randint(5, 11, (k // GROUP, n), generator=gen, dtype=torch.int32)
-        w_ref = oracle.dequantize(packed, w_s, w_zp, BITS, BIAS, GROUP, torch.float16)  # offline, like the reference test
-        x = torch.randn((M, k), generator=gen).to(torch.float16)
-        layers.append((x, w_ref))
-    sample_bytes = sum(k * n * BITS // 8 + M * k * 2 for _, k, n in PROJECTIONS)  # one layer = 1/32 of a step
+    layer_sets = []
+    for _ in range(2):
+        layer = []
+        for name, k, n in PROJECTIONS:
+            packed = torch.randint(-(1 << 31), (1 << 31) - 1, (k // 8, n), generator=gen, dtype=torch.int64).to(torch.int32)
+            w_s = (0.004 + 0.004 * torch.rand((k // GROUP, n), generator=gen)).to(torch.float16)
+            w_zp = torch.randint(5, 11, (k // GROUP, n), generator=gen, dtype=torch.int32)
+            w_ref = oracle.dequantize(packed, w_s, w_zp, BITS, BIAS, GROUP, torch.float16)  # offline, like the reference test
+            x = torch.randn((M, k), generator=gen).to(torch.float16)
+            layer.append((x, w_ref))
+        layer_sets.append(layer)
+    layer_bytes = sum(k * n * BITS // 8 + M * k * 2 for _, k, n in PROJECTIONS)
 
-    def one():
-        for x, w_ref in layers:
+    def one_layer(i):
+        for x, w_ref in layer_sets[i & 1]:
             oracle.reference_test_expression(x, w_ref)  # torch.matmul(a, w_ref), tests/mixed_precision_gemm_test.py:70
 
+    def one_step():
+        for i in range(layers_per_step):
+            one_layer(i)
+
+    t0 = time.perf_counter()
+    one_layer(0)
+    one_layer(1)
+    per_layer = (time.perf_counter() - t0) / 2
+    # keep the whole run inside the time budget: fewer timed steps if the host is slow (reported in `steps`)
+    est_step = per_layer * layers_per_step
+    steps = max(1, min(steps, int(budget_s / max(est_step, 1e-6)) - warmup))
+    warmup = max(0, min(warmup, int(0.25 * budget_s / max(est_step, 1e-6))))
     for _ in range(warmup):
-        one()
+        one_step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        one()
+        one_step()
     dt = (time.perf_counter() - t0) / steps
     return {
-        "value": sample_bytes / dt / 1e9,
+        "value": layer_bytes * layers_per_step / dt / 1e9,
         "unit": "GB/s",
         "cores": threads,
         "host_cpus": os.cpu_count(),
         "kind": "port",
-        "sample": "one Llama-3-8B layer's four M=1 projections per step (1/32 of the GPU step), fp16 torch.matmul(x, w_ref) "
-        "with w_ref pre-dequantised offline exactly as the reference test does; rate metric, so no rescaling",
-        "ms_per_sample": dt * 1e3,
+        "sample": f"{layers_per_step} layers x 4 M=1 projections per step (the GPU arm's step has {LAYERS}), fp16 torch.matmul(x, w_ref) with "
+        "w_ref pre-dequantised offline exactly as the reference test does, two distinct layers' weights cycled (872 MB); "
+        f"torch.set_num_threads({threads}), no core pinning",
+        "ms_per_step": dt * 1e3,
+        "steps": steps,
+        "warmup": warmup,
     }
 
 
@@ -170,23 +195,23 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 50))
-    res = cpu_reference(steps, max(1, min(args.warmup, 3)))
+    res = cpu_reference(args.steps, args.warmup)
     line = {
         "impl": "reference",
         "metric": METRIC,
         "value": res["value"],
         "unit": "GB/s",
         "n_gpus": args.gpus,
-        "steps": steps,
-        "warmup": max(1, min(args.warmup, 3)),
-        "ms_per_step": res["ms_per_sample"],
+        "steps": res["steps"],
+        "warmup": res["warmup"],
+        "ms_per_step": res["ms_per_step"],
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "device": "host CPU", "l2": "n/a"},
+        "config": {"workload": WORKLOAD, "M": M, "device": "host CPU", "l2": "n/a (872 MB of fp16 weights cycled through the host caches)",
+                   "sample": res["sample"]},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")},
         "e2e": {"value": res["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -370,9 +395,26 @@ def run_gpu_arm(args) -> None:
     h2d = sum(x.numel() * 2 for x in xs)
     d2h = out_dev.numel() * 2
 
+    # ---- BASELINE config 5 (70B FFN, N-sharded, strong scaling): every rank takes part ------------------------------
+    peak, peak_src, peaks = measured_peaks()
+    used_graph = graph is not None
+    d2h = out_dev.numel() * 2
+    cfg5 = None
+    prefill = prefill_probe(dev, peaks) if (world == 1 and rank == 0) else None  # before the sustained config-5 load: a burst figure
+    if not args.no_config5:
+        # release the 8B model first (rebinding, not `del`: the step closures above capture these names)
+        weights.clear()
+        outs.clear()
+        out_views.clear()
+        if sharded is not None:
+            sharded.clear()
+        out_dev = None
+        graph = None
+        torch.cuda.empty_cache()
+        cfg5 = config5_probe(world, rank, dev, peaks)
+
     # ---- report --------------------------------------------------------------------------------------------------
     if rank == 0:
-        peak, peak_src, peaks = measured_peaks()
         per_gpu = value / world
         traffic = None
         tp = ROOT / "profiles" / "traffic.json"
@@ -394,7 +436,7 @@ def run_gpu_arm(args) -> None:
             "config": {
                 "workload": WORKLOAD,
                 "M": M,
-                "launch": ("cuda-graph replay of the 128 GEMV launches" if graph is not None else "eager python launches")
+                "launch": ("cuda-graph replay of the 128 GEMV launches" if used_graph else "eager python launches")
                 + ("" if args.no_pdl else ", programmatic dependent launch"),
                 "l2": "inputs larger than L2: 3.49 GB of packed weights per step vs 126 MB L2",
                 "sharding": "none" if world == 1 else (f"N-sharded x{world}, NCCL all_gather_into_tensor after every GEMM (async: the gather of GEMM i overlaps GEMM i+1)" if args.nccl_gather else f"N-sharded x{world}, fused gather: every GEMV kernel stores its slice into all {world} ranks' gather buffers (P2P over NVLink, cb200_mpgemm_push), one cross-GPU barrier per token"),
@@ -424,10 +466,12 @@ def run_gpu_arm(args) -> None:
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(),
         }
-        if world == 1:
-            line["prefill"] = prefill_probe(dev, peaks)
+        if cfg5 is not None:
+            line["config5_70b_ffn"] = cfg5
+        if prefill is not None:
+            line["prefill"] = prefill
         if world == 1 and not args.no_cpu_baseline:
-            res = cpu_reference(steps=5, warmup=1)
+            res = cpu_reference(steps=3, warmup=1, layers_per_step=8, budget_s=25.0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -437,6 +481,128 @@ def run_gpu_arm(args) -> None:
         dist.barrier()
         torch.cuda.synchronize()
         os._exit(0)
+
+
+def config5_probe(world: int, rank: int, dev, peaks: dict) -> dict:
+    """BASELINE config 5: Llama-3-70B W4A16 FFN (K=8192, N=28672, uint4 + int32 zero-points, g128, fp16), the weight
+    column-(N-)sharded over the `world` GPUs -- STRONG scaling: the layer is fixed, every rank owns N/world columns -- with an
+    all-gather of the outputs so that every rank ends up with the full [M, N].  Reported per BASELINE.md section 3:
+    compute-only (the rank's shard GEMM), gather-only, and end to end, CUDA-event timed, max over ranks, cold L2 (rotating
+    weight copies > 2 x L2).
+      M = 1    : the gather is FUSED into the GEMV (cb200_mpgemm_push: the kernel's epilogue stores its slice into every rank's
+                 buffer over NVLink) and made visible by a device-side cross-GPU barrier after EVERY GEMV (per-GEMM visibility);
+                 gather-only = one NCCL all_gather_into_tensor of the same 57 KB, for comparison.
+      M = 4096 : tcgen05 GEMM on the shard + NCCL all_gather_into_tensor of the 235 MB output, software-pipelined (the gather of
+                 GEMM i overlaps GEMM i+1)."""
+    import torch
+    import torch.distributed as dist
+
+    from conch_b200 import _lib, quant_utils
+    from conch_b200.sharded import ShardedMixedPrecisionLinear
+
+    lib = _lib.load()
+    k, n = 8192, 28672
+    n_local = n // world
+    st = quant_utils.scalar_types.uint4
+    shard_bytes = k * n_local // 2
+    copies = max(3, min(24, int(2.2 * 126e6 / shard_bytes) + 1))
+    layers = [ShardedMixedPrecisionLinear(*quant_utils.random_packed_weights(k, n_local, st, GROUP, torch.float16, dev, seed=900 + 31 * rank + i),
+                                          BITS, BIAS, GROUP, already_sharded=True) for i in range(copies)]  # fmt: skip
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tc = float(peaks.get("bf16_tflops", 1590.0))
+
+    def timed(fn, iters: int, graph: bool) -> float:
+        """average microseconds per call of fn(i), max over ranks"""
+        stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(stream):
+            for i in range(copies):
+                fn(i)
+            stream.synchronize()
+            g = None
+            if graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    for i in range(copies):
+                        fn(i)
+                g.replay()
+                stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            reps = max(1, iters // copies)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                if g is not None:
+                    g.replay()
+                else:
+                    for i in range(copies):
+                        fn(i)
+            e1.record(stream)
+            e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / (reps * copies)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    res = {"workload": f"llama3-70b-w4a16-ffn K={k} N={n} sharded over {world} GPU(s) along N (strong scaling), uint4+zp_int32, g128, fp16",
+           "weight_copies_rotated": copies}  # fmt: skip
+    for m in (1, 4096):
+        x = torch.randn((m, k), device=dev, dtype=torch.float16)
+        algo_bytes = k * n // 2 + m * k * 2
+        flop = 2.0 * m * k * n
+        t_roof = max(flop / (world * tc * 1e12), (k * n // 2 + world * m * k * 2) / (world * hbm * 1e9)) * 1e6
+        row = {"roofline_us": t_roof, "gathered_output_bytes": m * n * 2}
+        if m == 1:
+            lib.cb200_set_pdl(1)
+            outs = [torch.empty((m, n_local), device=dev, dtype=torch.float16) for _ in range(copies)]
+            row["compute_us"] = timed(lambda i: layers[i].local(x, out=outs[i]), 400, graph=True)
+            if world > 1:
+                def fused(i):
+                    layers[i].pushed(x)
+                    layers[i].sync()  # per-GEMM visibility: every rank may read the full [1, N] of GEMV i after this
+
+                row["e2e_us"] = timed(fused, 400, graph=True)
+                gbuf = torch.empty((world * m, n_local), device=dev, dtype=torch.float16)
+                row["gather_us"] = timed(lambda i: dist.all_gather_into_tensor(gbuf, outs[i]), 200, graph=False)
+                row["gather"] = "fused into the GEMV epilogue (P2P stores over NVLink) + one device-side barrier per GEMV; gather_us = a stand-alone NCCL all_gather of the same bytes"
+            else:
+                row["e2e_us"] = row["compute_us"]
+                row["gather_us"] = 0.0
+            lib.cb200_set_pdl(0)
+        else:
+            out = torch.empty((m, n_local), device=dev, dtype=torch.float16)
+            row["compute_us"] = timed(lambda i: layers[i].local(x, out=out), 48, graph=False)
+            if world > 1:
+                outs2 = [torch.empty((m, n_local), device=dev, dtype=torch.float16) for _ in range(2)]
+                gbufs = [torch.empty((world * m, n_local), device=dev, dtype=torch.float16) for _ in range(2)]
+                row["gather_us"] = timed(lambda i: dist.all_gather_into_tensor(gbufs[0], outs2[0]), 24, graph=False)
+                pending = [None, None]
+
+                def piped(i):
+                    b = i & 1
+                    if pending[b] is not None:
+                        pending[b].wait()  # buffer b's previous gather is done: its GEMM output may be overwritten
+                    layers[i].local(x, out=outs2[b])
+                    pending[b] = dist.all_gather_into_tensor(gbufs[b], outs2[b], async_op=True)
+
+                row["e2e_us"] = timed(piped, 48, graph=False)
+                for w in pending:
+                    if w is not None:
+                        w.wait()
+                row["gather"] = "NCCL all_gather_into_tensor, double-buffered: the gather of GEMM i overlaps GEMM i+1"
+            else:
+                row["e2e_us"] = row["compute_us"]
+                row["gather_us"] = 0.0
+        row["tflops_e2e"] = flop / row["e2e_us"] / 1e6
+        row["GBps_e2e"] = algo_bytes / row["e2e_us"] / 1e3
+        row["roofline_frac_e2e"] = t_roof / row["e2e_us"]
+        row["roofline_frac_compute"] = t_roof / row["compute_us"]
+        res[f"M{m}"] = row
+        del x
+    del layers
+    torch.cuda.empty_cache()
+    return res
 
 
 def prefill_probe(dev, peaks: dict) -> dict:
@@ -492,6 +658,7 @@ def main() -> None:
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: NCCL all-gather after every GEMM instead of the fused P2P push")
     ap.add_argument("--no-graph", action="store_true", help="time eager Python launches instead of a CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 70B-FFN (BASELINE config 5) strong-scaling measurement")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between the GEMVs")
     args = ap.parse_args()
     if args.warmup < 3:

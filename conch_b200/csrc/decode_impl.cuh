@@ -482,11 +482,19 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   if (prev != unsigned(S - 1)) return;
   __threadfence();  // last arriver: every other slab's partial is visible now
   const float* base = ws_partial + size_t(cb) * S * (M * CW);
-  for (int e = lane; e < M * CW; e += 32) {
-    float v = 0.f;
-    for (int s = 0; s < S; ++s) v += __ldcg(base + size_t(s) * (M * CW) + e);
-    const int m = e / CW, lc = e - m * CW;
-    store_out_all<A>(p, size_t(m) * N + cb * CW + lc, v);
+  // each lane owns 8 consecutive columns of one row (4 lanes per row): the result leaves as two 8-byte vector stores per
+  // destination (fp16 / bf16) -- for cb200_mpgemm_push that is 4x fewer NVLink writes per peer than element stores
+  for (int e = lane; e < M * (CW / 8); e += 32) {
+    const int m = e / (CW / 8), lc = (e - m * (CW / 8)) * 8;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    for (int s = 0; s < S; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(base + size_t(s) * (M * CW) + m * CW + lc);
+      const float4 a = __ldcg(src), b = __ldcg(src + 1);
+      v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
+      v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
+    }
+    store_out4_all(p, size_t(m) * N + cb * CW + lc, v0);
+    store_out4_all(p, size_t(m) * N + cb * CW + lc + 4, v1);
   }
   if (lane == 0) ws_counter[cb] = 0u;  // leave the counter clean for the next launch
 }

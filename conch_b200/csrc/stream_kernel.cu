@@ -106,7 +106,8 @@ static StreamPlan stream_plan(int mrows, int K, int N, int bits, int g, int zp_k
 bool stream_supported(const Problem& p, int bits, int act_dtype) {
   if (encode_fn() == nullptr) return false;
   if (act_dtype == CB200_BF16 && bits == 8) return false;  // no magic-number operand: decode_kernel's per-weight dequant
-  return p.K % 64 == 0 && p.N % 64 == 0 && p.g % 64 == 0;
+  const int ks = 16 * (32 / bits);                         // a stage is 16 packed rows: K must be a whole number of stages
+  return p.K % ks == 0 && p.N % 64 == 0 && p.g % 64 == 0;
 }
 
 static size_t stream_partial_bytes(const StreamPlan& pl, int mrows) {
@@ -114,6 +115,7 @@ static size_t stream_partial_bytes(const StreamPlan& pl, int mrows) {
 }
 
 size_t stream_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits) {
+  if (K % (16 * (32 / bits)) != 0) return 0;  // not a streaming-kernel shape (stream_supported)
   const int rows = M < 16 ? int(M) : 16;
   const StreamPlan pl = stream_plan(rows, int(K), int(N), bits, int(K), CB200_ZP_I32, false);
   return size_t(CB200_WORKSPACE_COUNTER_BYTES) + stream_partial_bytes(pl, rows);
