@@ -489,8 +489,9 @@ def config5_probe(world: int, rank: int, dev, peaks: dict) -> dict:
     all-gather of the outputs so that every rank ends up with the full [M, N].  Reported per BASELINE.md section 3:
     compute-only (the rank's shard GEMM), gather-only, and end to end, CUDA-event timed, max over ranks, cold L2 (rotating
     weight copies > 2 x L2).
-      M = 1    : the gather is FUSED into the GEMV (cb200_mpgemm_push: the kernel's epilogue stores its slice into every rank's
-                 buffer over NVLink) and made visible by a device-side cross-GPU barrier after EVERY GEMV (per-GEMM visibility);
+      M = 1    : the gather is FUSED into the GEMV (cb200_mpgemm_push_signal: the kernel's epilogue stores its slice into every
+                 rank's buffer over NVLink and then raises a completion flag on every GPU); every GEMV is followed by a wait for
+                 all ranks' flags, i.e. the time includes per-GEMM visibility of the full [1, N] on every rank;
                  gather-only = one NCCL all_gather_into_tensor of the same 57 KB, for comparison.
       M = 4096 : tcgen05 GEMM on the shard + NCCL all_gather_into_tensor of the 235 MB output, software-pipelined (the gather of
                  GEMM i overlaps GEMM i+1)."""
@@ -559,13 +560,15 @@ def config5_probe(world: int, rank: int, dev, peaks: dict) -> dict:
             row["compute_us"] = timed(lambda i: layers[i].local(x, out=outs[i]), 400, graph=True)
             if world > 1:
                 def fused(i):
-                    layers[i].pushed(x)
-                    layers[i].sync()  # per-GEMM visibility: every rank may read the full [1, N] of GEMV i after this
+                    layers[i].pushed_signalled(x)  # the kernel raises this rank's completion flag on every GPU ...
+                    layers[i].wait()               # ... and the stream continues once all ranks' flags of GEMV i are here
 
                 row["e2e_us"] = timed(fused, 400, graph=True)
                 gbuf = torch.empty((world * m, n_local), device=dev, dtype=torch.float16)
                 row["gather_us"] = timed(lambda i: dist.all_gather_into_tensor(gbuf, outs[i]), 200, graph=False)
-                row["gather"] = "fused into the GEMV epilogue (P2P stores over NVLink) + one device-side barrier per GEMV; gather_us = a stand-alone NCCL all_gather of the same bytes"
+                row["gather"] = ("fused into the GEMV epilogue (P2P vector stores over NVLink); per-GEMV visibility through completion flags "
+                                 "raised by the kernel on every GPU + a one-warp wait (no barrier, no NCCL); gather_us = a stand-alone NCCL "
+                                 "all_gather of the same bytes, for comparison")
             else:
                 row["e2e_us"] = row["compute_us"]
                 row["gather_us"] = 0.0

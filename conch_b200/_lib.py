@@ -29,6 +29,8 @@ EXPORTS = (
     "cb200_mpgemm_workspace_bytes",
     "cb200_mpgemm",
     "cb200_mpgemm_push",
+    "cb200_mpgemm_push_signal",
+    "cb200_wait_flags",
     "cb200_last_variant",
     "cb200_last_launch_count",
     "cb200_dequantize",
@@ -85,6 +87,10 @@ def load() -> ctypes.CDLL:
         ]  # fmt: skip
         lib.cb200_mpgemm_push.restype = c_int
         lib.cb200_mpgemm_push.argtypes = lib.cb200_mpgemm.argtypes + [ctypes.POINTER(c_void_p), c_int]  # peer_out, num_peers
+        lib.cb200_mpgemm_push_signal.restype = c_int
+        lib.cb200_mpgemm_push_signal.argtypes = lib.cb200_mpgemm_push.argtypes + [ctypes.POINTER(c_void_p), c_void_p]
+        lib.cb200_wait_flags.restype = c_int
+        lib.cb200_wait_flags.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
         lib.cb200_dequantize.restype = c_int
         lib.cb200_dequantize.argtypes = [
             c_void_p, c_void_p, c_void_p, c_void_p,

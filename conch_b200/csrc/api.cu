@@ -190,6 +190,24 @@ int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, co
                       int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
                       int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
                       void* stream, void* const* peer_out, int num_peers) {
+  return cb200_mpgemm_push_signal(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, weight_bias, group_size, act_dtype,
+                                  out_dtype, zp_kind, zp_is_scalar, workspace, workspace_bytes, variant, stream, peer_out, num_peers,
+                                  nullptr, nullptr);
+}
+
+int cb200_wait_flags(const void* flags, int count, void* expected, void* stream) {
+  if (!flags || !expected || count < 1 || count > 32) {
+    set_error("cb200_wait_flags: null pointer or count=%d outside 1..32", count);
+    return CB200_ERR_ARG;
+  }
+  return launch_wait_flags(reinterpret_cast<const uint32_t*>(flags), count, reinterpret_cast<uint32_t*>(expected),
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M,
+                             int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
+                             int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
+                             void* stream, void* const* peer_out, int num_peers, void* const* peer_flags, void* local_flag) {
   tls_last_variant = 0;
   tls_last_launches = 0;
   int rc = check_device();
@@ -227,6 +245,20 @@ int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, co
     }
     p.peer_out[i] = peer_out[i];
   }
+  if (local_flag != nullptr) {
+    if (num_peers > 0 && !peer_flags) {
+      set_error("cb200_mpgemm_push_signal: peer_flags is null");
+      return CB200_ERR_ARG;
+    }
+    for (int i = 0; i < num_peers; ++i) {
+      if (!peer_flags[i] || (reinterpret_cast<uintptr_t>(peer_flags[i]) & 3u)) {
+        set_error("peer_flags[%d] is null or not 4-byte aligned", i);
+        return CB200_ERR_ARG;
+      }
+      p.peer_flag[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+    }
+    p.local_flag = reinterpret_cast<uint32_t*>(local_flag);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   int chosen = variant;
@@ -241,6 +273,10 @@ int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, co
   if (num_peers > 0 && chosen != CB200_DECODE_MMA && chosen != CB200_DECODE_STREAM && chosen != CB200_DECODE_TCS) {
     // the fused push lives in the decode kernels' (tiny) epilogue; big outputs are bandwidth-bound: all-gather them
     set_error("cb200_mpgemm_push: only the decode kernels (M <= 16) store to peers; use an all-gather for M=%lld", (long long)M);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (p.local_flag != nullptr && (chosen != CB200_DECODE_MMA || M > 16)) {
+    set_error("cb200_mpgemm_push_signal: the completion flags are raised by the register-window decode kernel only (M <= 16 in one pass)");
     return CB200_ERR_UNSUPPORTED;
   }
   int launches = 0;

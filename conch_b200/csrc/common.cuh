@@ -29,7 +29,28 @@ struct Problem {
   int out_dtype;    // cb200_dtype
   int n_peers;      // cb200_mpgemm_push: the result is also stored into peer_out[0 .. n_peers) (same [M, N] layout)
   void* peer_out[CB200_MAX_PEERS];
+  // cb200_mpgemm_push_signal: once the WHOLE result has been pushed, every peer_flag (a 32-bit counter in the peer's memory) and
+  // local_flag are incremented by one: per-GEMM visibility without a cross-GPU barrier, safe under CUDA-graph replay
+  uint32_t* peer_flag[CB200_MAX_PEERS];
+  uint32_t* local_flag;
 };
+
+// Called by a warp that has finished (stored and pushed) one 32-column block of a cb200_mpgemm_push_signal GEMV: system-scope
+// fence, count the block, and -- as the last block of the grid -- raise the flags.  `done` is a self-resetting counter.
+__device__ __forceinline__ void push_signal_block_done(const Problem& p, unsigned int* done, unsigned int total_blocks, int lane) {
+  if (p.local_flag == nullptr) return;
+  __threadfence_system();  // this warp's stores to the peers are performed system-wide before the count
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == total_blocks - 1u) {
+      *done = 0u;
+      __threadfence_system();
+      for (int i = 0; i < p.n_peers; ++i) atomicAdd_system(p.peer_flag[i], 1u);
+      atomicAdd_system(p.local_flag, 1u);
+    }
+  }
+}
 
 void set_error(const char* fmt, ...);
 
@@ -56,6 +77,7 @@ bool tc_supported(const Problem& p, int bits);
 int launch_stream(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 size_t stream_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
 bool stream_supported(const Problem& p, int bits, int act_dtype);
+int launch_wait_flags(const uint32_t* flags, int count, uint32_t* expected, cudaStream_t stream);
 int launch_tcs(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 size_t tcs_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
 bool tcs_supported(const Problem& p, int bits, int act_dtype);

@@ -40,6 +40,7 @@ struct DecodeGeom {
   int cta_x_bytes;    // per-CTA smem bytes of the shared x slab (the 4 warps of a CTA work on the same K slab)
   int cb_padded;      // column blocks rounded up to a multiple of 4 (whole CTAs per slab; padding warps only sync)
   int cta_aux_bytes;  // per-CTA smem after the x slab: chunk sums [m_rows][slab_k / 8] + group sums [ngroups][8] (fp32)
+  int scalar_push;    // debug (cb200_set_decode_tuning vec_words = 1): element stores to the peers instead of 8-byte vectors
 #ifdef CB200_TC_TRACE
   long long* trace;   // [CTAs][8] globaltimer stamps (debug builds only)
 #endif
@@ -456,6 +457,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
           store_out_all<A>(p, size_t(m + 1) * N + n + 1, acc[t][mt][3]);
         }
       }
+    push_signal_block_done(p, ws_counter + (CB200_WORKSPACE_COUNTER_BYTES / 4 - 1), unsigned(C), lane);
     return;
   }
   float* mine = ws_partial + (size_t(cb) * S + si) * (M * CW);
@@ -482,21 +484,31 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   if (prev != unsigned(S - 1)) return;
   __threadfence();  // last arriver: every other slab's partial is visible now
   const float* base = ws_partial + size_t(cb) * S * (M * CW);
-  // each lane owns 8 consecutive columns of one row (4 lanes per row): the result leaves as two 8-byte vector stores per
-  // destination (fp16 / bf16) -- for cb200_mpgemm_push that is 4x fewer NVLink writes per peer than element stores
-  for (int e = lane; e < M * (CW / 8); e += 32) {
-    const int m = e / (CW / 8), lc = (e - m * (CW / 8)) * 8;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    for (int s = 0; s < S; ++s) {
-      const float4* src = reinterpret_cast<const float4*>(base + size_t(s) * (M * CW) + m * CW + lc);
-      const float4 a = __ldcg(src), b = __ldcg(src + 1);
-      v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
-      v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
+  if (p.n_peers > 0 && !geo.scalar_push) {
+    // multi-GPU push: each lane owns 8 consecutive columns of one row (4 lanes per row) and the result leaves as two 8-byte
+    // vector stores per destination (fp16 / bf16) -- 4x fewer NVLink writes per peer than element stores
+    for (int e = lane; e < M * (CW / 8); e += 32) {
+      const int m = e / (CW / 8), lc = (e - m * (CW / 8)) * 8;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      for (int s = 0; s < S; ++s) {
+        const float4* src = reinterpret_cast<const float4*>(base + size_t(s) * (M * CW) + m * CW + lc);
+        const float4 a = __ldcg(src), b = __ldcg(src + 1);
+        v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
+        v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
+      }
+      store_out4_all(p, size_t(m) * N + cb * CW + lc, v0);
+      store_out4_all(p, size_t(m) * N + cb * CW + lc + 4, v1);
     }
-    store_out4_all(p, size_t(m) * N + cb * CW + lc, v0);
-    store_out4_all(p, size_t(m) * N + cb * CW + lc + 4, v1);
+  } else {
+    for (int e = lane; e < M * CW; e += 32) {
+      float v = 0.f;
+      for (int s = 0; s < S; ++s) v += __ldcg(base + size_t(s) * (M * CW) + e);
+      const int m = e / CW, lc = e - m * CW;
+      store_out_all<A>(p, size_t(m) * N + cb * CW + lc, v);
+    }
   }
   if (lane == 0) ws_counter[cb] = 0u;  // leave the counter clean for the next launch
+  push_signal_block_done(p, ws_counter + (CB200_WORKSPACE_COUNTER_BYTES / 4 - 1), unsigned(C), lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------

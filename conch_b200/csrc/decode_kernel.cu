@@ -189,7 +189,7 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
       set_error("decode kernel needs %zu workspace bytes, got %zu", need, ws_bytes);
       return CB200_ERR_WORKSPACE;
     }
-    if (size_t(pl.col_blocks) * sizeof(unsigned) > CB200_WORKSPACE_COUNTER_BYTES) {
+    if (size_t(pl.col_blocks + 1) * sizeof(unsigned) > CB200_WORKSPACE_COUNTER_BYTES) {  // (+1: the push-signal counter in the last slot)
       set_error("N=%d too large for the split-K counter area", p.N);
       return CB200_ERR_SHAPE;
     }
@@ -211,6 +211,7 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     geo.cta_x_bytes = pl.cta_x_bytes;
     geo.cb_padded = pl.cb_padded;
     geo.cta_aux_bytes = pl.cta_aux_bytes;
+    geo.scalar_push = g_decode_tuning.vec_words == 1;
 #ifdef CB200_TC_TRACE
     geo.trace = g_dec_trace;
 #endif

@@ -77,4 +77,30 @@ int launch_dequant(const Problem& p, int bits, int act_dtype, cudaStream_t strea
   return bits == 4 ? launch_dq<__nv_bfloat16, 4>(p, stream) : launch_dq<__nv_bfloat16, 8>(p, stream);
 }
 
+// ---- cb200_wait_flags: the consumer side of cb200_mpgemm_push_signal ------------------------------------------------------------
+// One warp.  `*expected` counts the waits done so far on this flag array (device memory, advanced by the kernel itself, so a
+// replayed CUDA graph keeps counting); lane i spins (system-scope acquire loads) until counter flags[i] has reached it.
+// Bounded: a lost signal becomes a trap (launch error), not a hung GPU.
+__global__ void wait_flags_kernel(const uint32_t* flags, int count, uint32_t* expected) {
+  const int lane = threadIdx.x;
+  const uint32_t want = *expected + 1u;
+  if (lane < count) {
+    const uint32_t* f = flags + lane;
+    for (unsigned spin = 0;; ++spin) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (int32_t(v - want) >= 0) break;
+      if (spin > (1u << 28)) __trap();
+    }
+  }
+  __syncwarp();
+  if (lane == 0) *expected = want;
+}
+
+int launch_wait_flags(const uint32_t* flags, int count, uint32_t* expected, cudaStream_t stream) {
+  wait_flags_kernel<<<1, 32, 0, stream>>>(flags, count, expected);
+  CB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace cb200

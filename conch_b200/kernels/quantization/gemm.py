@@ -104,6 +104,7 @@ def mixed_precision_gemm_launcher(
     *,
     variant: int = _lib.AUTO,
     peer_out_ptrs: Sequence[int] | None = None,
+    signal: tuple[Sequence[int], int] | None = None,
 ) -> None:
     """Enqueue out = x @ dequant(W) on the current CUDA stream.  Never synchronises.
 
@@ -144,9 +145,15 @@ def mixed_precision_gemm_launcher(
         stream,
     )  # fmt: skip
     entry = lib.cb200_mpgemm
-    if peer_out_ptrs:
+    if peer_out_ptrs or signal is not None:
+        peers = list(peer_out_ptrs or ())
         entry = lib.cb200_mpgemm_push
-        args = args + ((ctypes.c_void_p * len(peer_out_ptrs))(*peer_out_ptrs), len(peer_out_ptrs))
+        args = args + ((ctypes.c_void_p * max(len(peers), 1))(*peers), len(peers))
+        if signal is not None:
+            # (peer flag pointers, local flag pointer): the kernel bumps the counters once the whole result is pushed
+            peer_flags, local_flag = signal
+            entry = lib.cb200_mpgemm_push_signal
+            args = args + ((ctypes.c_void_p * max(len(peer_flags), 1))(*peer_flags), local_flag)
     if index != torch.cuda.current_device():
         with torch.cuda.device(device):
             rc = entry(*args)

@@ -180,12 +180,14 @@ def mixed_precision_gemm(
     variant: int = _lib.AUTO,
     out: torch.Tensor | None = None,
     peer_out_ptrs: Sequence[int] | None = None,
+    signal: tuple[Sequence[int], int] | None = None,
 ) -> torch.Tensor:
     """Mixed precision GEMM: `x[M,K] @ dequant(w_q_packed[K/pf,N], w_s, w_zp) -> [M,N]`.
 
     Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus three optional keywords:
     `variant` forces a kernel family (debug / benchmarking), `out` reuses a caller-owned output buffer, `peer_out_ptrs`
-    (multi-GPU, decode regime: M <= 8) lists peer-GPU buffers the kernel also stores the result to (conch_b200/sharded.py).
+    (multi-GPU, decode regime: M <= 8) lists peer-GPU buffers the kernel also stores the result to, and `signal` = (peer flag
+    pointers, local flag pointer) makes it bump completion counters on every GPU afterwards (conch_b200/sharded.py).
     """
     _require_device(x, w_q_packed, w_s, w_zp)
     metadata = create_mixed_precision_metadata(
@@ -203,7 +205,7 @@ def mixed_precision_gemm(
         raise ValueError("`out` must be a contiguous [M, N] tensor of the output dtype")
     if metadata.m_dim == 0:
         return out
-    mixed_precision_gemm_launcher(out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs)
+    mixed_precision_gemm_launcher(out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal)
     return out
 
 

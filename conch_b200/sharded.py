@@ -65,6 +65,7 @@ class ShardedMixedPrecisionLinear:
         self._gather_buf: torch.Tensor | None = None
         self._local_buf: torch.Tensor | None = None
         self._symm: dict[tuple[int, torch.dtype], tuple[torch.Tensor, object, list[int]]] = {}
+        self._flags: tuple[torch.Tensor, object, list[int]] | None = None
 
     def local(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         """This rank's `[M, N/G]` slice of the output (no communication)."""
@@ -108,6 +109,50 @@ class ShardedMixedPrecisionLinear:
             peers = [int(hdl.buffer_ptrs[p]) + slot for p in range(self.world) if p != self.rank]
             self._symm[key] = (buf, hdl, peers)
         return self._symm[key]
+
+    def _flag_array(self, device: torch.device):
+        """`[world]` uint32 completion flags in symmetric memory (slot r is written by rank r's kernels).  COLLECTIVE on first use."""
+        if self._flags is None:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            flags = symm_mem.empty((max(self.world, 8) + 8,), dtype=torch.int32, device=device)  # [world] counters + the wait's own
+            flags.zero_()
+            group = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(flags, group.group_name)
+            hdl.barrier(channel=1)  # everybody's flags are zero before anybody signals
+            peer_flags = [int(hdl.buffer_ptrs[p]) + 4 * self.rank for p in range(self.world) if p != self.rank]
+            self._flags = (flags, hdl, peer_flags)
+        return self._flags
+
+    def pushed_signalled(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
+        """`pushed()` with PER-GEMM visibility and no cross-GPU barrier: when the whole `[M, N/G]` slice has reached every rank,
+        the kernel raises this rank's completion flag on every GPU (`cb200_mpgemm_push_signal`).  `wait()` then blocks the
+        CURRENT STREAM (not the host) until all ranks' flags of this call have arrived: the gathered `[G, M, N/G]` buffer is
+        complete, with the latency of one NVLink store instead of a barrier or an NCCL collective."""
+        m = x.shape[0]
+        if self.world == 1:
+            return self.local(x, **kwargs).unsqueeze(0)
+        if m > self.PUSH_MAX_ROWS:
+            raise NotImplementedError(f"pushed_signalled() is for the decode regime (M <= {self.PUSH_MAX_ROWS}); use gathered() for M={m}")
+        out_dtype = kwargs.get("output_dtype") or x.dtype
+        buf, _, peers = self._symmetric(m, out_dtype, x.device)
+        flags, _, peer_flags = self._flag_array(x.device)
+        self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size, out=buf[self.rank],
+                   peer_out_ptrs=peers, signal=(peer_flags, flags.data_ptr() + 4 * self.rank), **kwargs)  # fmt: skip
+        return buf
+
+    def wait(self) -> None:
+        """Enqueue (current stream) the wait for every rank's completion counter of the latest `pushed_signalled()` call.
+        Exactly ONE wait per pushed_signalled() on every rank (the counters count both); graph-capturable and replay-safe."""
+        if self.world == 1 or self._flags is None:
+            return
+        from conch_b200 import _lib
+
+        flags = self._flags[0]
+        stream = torch.cuda.current_stream(flags.device).cuda_stream
+        with torch.cuda.device(flags.device):
+            expected = flags.data_ptr() + 4 * max(self.world, 8)  # the wait's own counter lives behind the [world] flags
+            _lib.raise_for_status(_lib.load().cb200_wait_flags(flags.data_ptr(), self.world, expected, stream))
 
     def pushed(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         """GEMM on the shard whose epilogue stores the `[M, N/G]` result into slot `rank` of EVERY rank's gather buffer

@@ -111,6 +111,25 @@ CB200_API int cb200_mpgemm_push(const void* x, const void* w_q_packed, const voi
                  void* workspace, size_t workspace_bytes,
                  int variant, void* stream, void* const* peer_out, int num_peers);
 
+/* cb200_mpgemm_push with per-GEMM visibility (no cross-GPU barrier): once the WHOLE [M, N] result has been stored to `out`
+ * and to every peer, the kernel INCREMENTS local_flag and peer_flags[i] by one (system-scope atomics) -- 32-bit counters,
+ * peer_flags[i] a device pointer into peer i's memory (typically slot `rank` of a [world] uint32 array in symmetric memory,
+ * zero-initialised).  A consumer on any GPU that needs the gathered output waits until all `world` counters of ITS array have
+ * reached the number of signalled GEMVs so far: cb200_wait_flags keeps that number in `*expected` (device memory, zero-
+ * initialised, advanced by the wait itself), so a signalled GEMV followed by ONE wait on every rank is safe to capture in a
+ * CUDA graph and replay.  Register-window decode kernel only (AUTO: M <= 8; M <= 16 with variant = CB200_DECODE_MMA).
+ * local_flag == NULL: plain cb200_mpgemm_push. */
+CB200_API int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
+                 int64_t M, int64_t K, int64_t N,
+                 int weight_size_bits, int weight_bias, int64_t group_size,
+                 int act_dtype, int out_dtype, int zp_kind, int zp_is_scalar,
+                 void* workspace, size_t workspace_bytes,
+                 int variant, void* stream, void* const* peer_out, int num_peers,
+                 void* const* peer_flags, void* local_flag);
+/* Enqueue a one-warp kernel on `stream` that advances *expected by one and returns once flags[0 .. count) have all reached it
+ * (count <= 32). */
+CB200_API int cb200_wait_flags(const void* flags, int count, void* expected, void* stream);
+
 /* Which kernel family the last cb200_mpgemm call on this thread dispatched to (a cb200_variant), and how many
  * kernel launches it enqueued.  Used by tests and by bench.py's `gpu_launches` accounting. */
 CB200_API int cb200_last_variant(void);
@@ -127,7 +146,7 @@ CB200_API int cb200_dequantize(const void* w_q_packed, const void* w_s, const vo
  *   warps_n   1: dequantise every weight before the MMA (W bits equal the reference's w_ref); 0/2: fused operands (default)
  *   warps_k   CTAs per SM assumed resident when the split count is chosen
  *   split_k   forced number of K slabs per 32-column block (rounded to a legal divisor)
- *   vec_words unused */
+ *   vec_words 1: element (2-byte) stores to the peers in cb200_mpgemm_push instead of 8-byte vectors (A/B measurements) */
 CB200_API void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_words);
 /* Debug/tuning knobs for the tcgen05 family: m_tile (MMA N: 16..256, 0 = heuristic), split_k (0 = heuristic). */
 CB200_API void cb200_set_tc_tuning(int m_tile, int split_k);

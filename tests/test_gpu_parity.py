@@ -388,6 +388,45 @@ def test_push_epilogue_writes_every_peer_buffer(m, k, n):
         assert torch.equal(t, plain)
 
 
+def test_push_signal_counts_and_wait_is_replay_safe():
+    """cb200_mpgemm_push_signal: after the whole result has been pushed the kernel bumps the local and the peer counters;
+    cb200_wait_flags keeps its own count on the device, so a (GEMV, wait) pair replays from a CUDA graph.  Single GPU: the
+    "peers" are buffers of the same device."""
+    lib = _lib.load()
+    p = oracle.make_problem(3, 2048, 1024, "uint4", 128, torch.float16, True, seed=9)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    want = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128)
+    peers = [torch.zeros_like(want) for _ in range(2)]
+    flags = torch.zeros(16, dtype=torch.int32, device="cuda")  # [0..2]: counters of "rank" 0 (local), 1, 2; [8]: the wait's own count
+    out = torch.empty_like(want)
+    sig = ([flags.data_ptr() + 4, flags.data_ptr() + 8], flags.data_ptr())
+
+    def call():
+        mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, out=out, peer_out_ptrs=[t.data_ptr() for t in peers], signal=sig)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.raise_for_status(lib.cb200_wait_flags(flags.data_ptr(), 3, flags.data_ptr() + 32, stream))
+
+    call()
+    torch.cuda.synchronize()
+    assert flags[:3].tolist() == [1, 1, 1] and int(flags[8]) == 1
+    for t in peers + [out]:
+        assert torch.equal(bits(t), bits(want))
+    call()
+    torch.cuda.synchronize()
+    assert flags[:3].tolist() == [2, 2, 2] and int(flags[8]) == 2
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            call()
+        for _ in range(5):
+            g.replay()
+    torch.cuda.synchronize()
+    assert flags[:3].tolist() == [7, 7, 7] and int(flags[8]) == 7
+    with pytest.raises(NotImplementedError):  # the flags are raised by the register-window decode kernel only
+        mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, out=out, variant=_lib.DECODE_TCS, peer_out_ptrs=[peers[0].data_ptr()], signal=sig)
+
+
 def test_push_epilogue_is_decode_only():
     from conch_b200 import _lib, quant_utils
 

@@ -51,6 +51,15 @@ def _worker(rank: int, world: int, port: int, ret) -> None:
                 layer.sync()
                 torch.cuda.synchronize()
                 assert torch.equal(buf.permute(1, 0, 2).reshape(m, -1), mixed_precision_gemm(-x, wq, ws, wzp, 4, 0, 128))
+                # per-GEMM visibility without a barrier: the kernel bumps a completion counter on every GPU, wait() spins on them
+                layer.sync()
+                for sign in (1.0, -1.0, 1.0):
+                    buf = layer.pushed_signalled(sign * x)
+                    layer.wait()
+                    got = buf.permute(1, 0, 2).reshape(m, -1).clone()
+                    layer.sync()  # (the test re-uses the buffer right away: nobody may still be reading it)
+                    torch.cuda.synchronize()
+                    assert torch.equal(got, mixed_precision_gemm(sign * x, wq, ws, wzp, 4, 0, 128)), f"pushed_signalled != single at M={m}"
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
