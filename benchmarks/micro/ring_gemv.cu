@@ -220,20 +220,16 @@ __global__ void __launch_bounds__(32 * (2 * MAXNW + 1), 1) ring_gemv(const __gri
   STAMP(0);
   const int nthr = 32 * NGRP * nw;  // consumer threads
   if (warp == NGRP * nw) {          // the producer warp sets the barriers up, so that its first copies leave before anything else
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmw)) : "memory");
-      for (int i = 0; i < g.ring; ++i) {
-        mbar_init(bar_full + 8 * i, 1);
-        mbar_init(bar_empty + 8 * i, nw);
-      }
-      if (S > 1) {
-        for (int w = rank, i = 0; w < nw; w += S, ++i) {  // the column groups (one per warp of a consumer group) this CTA reduces
-          mbar_init(bar_red + 8 * i, 1);
-          mbar_expect_tx(bar_red + 8 * i, uint32_t(S * NGRP) * uint32_t(M) * 128u);
-        }
-      }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmw)) : "memory");
+    if (lane < g.ring) {
+      mbar_init(bar_full + 8 * lane, 1);
+      mbar_init(bar_empty + 8 * lane, nw);
     }
+    if (S > 1 && rank + lane * S < nw) {  // the column groups (one per warp of a consumer group) this CTA reduces
+      mbar_init(bar_red + 8 * lane, 1);
+      mbar_expect_tx(bar_red + 8 * lane, uint32_t(S * NGRP) * uint32_t(M) * 128u);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     asm volatile("bar.arrive 2, %0;" ::"r"(nthr + 32) : "memory");
   } else {
@@ -241,38 +237,46 @@ __global__ void __launch_bounds__(32 * (2 * MAXNW + 1), 1) ring_gemv(const __gri
   }
   if (S > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // waited for just before the reduction
   const int QPB = g.QPB, N = g.N, BN = 32 * nw;
-  const int q_lo = int((long long)rank * QPB / S), q_hi = int((long long)(rank + 1) * QPB / S);
+  const int q_lo = rank * QPB / S, q_hi = (rank + 1) * QPB / S;
   const int qa0 = q_lo & ~3;                         // stage i covers the quads [qa0 + 4i, qa0 + 4i + 4) that lie in [q_lo, q_hi)
   const int nstages = (q_hi - qa0 + 3) >> 2;
   const int cols = min(BN, N - cb * BN);
   const uint32_t s_off = g.w_bytes, z_off = g.w_bytes + g.gps * BN * 2;
 
   if (warp == NGRP * nw) {
-    // ------------------------------------------------------------------ producer (one thread) ---------------------------
-    if (lane != 0) return;
+    // ------------------------------------------------------------------ producer -----------------------------------------
+    // The whole warp walks the stage list (every value below is warp-uniform, so it lives in uniform registers and the copy
+    // instructions take their operands from there); one elected lane issues the copies.
+    uint32_t leader = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     int slot = 0;
     uint32_t phase = 0;
-    bool first_round = true;
+    const uint32_t meta_bytes = uint32_t(cols) * 6u;
+    const char* sp = reinterpret_cast<const char*>(g.s + cb * BN);
+    const char* zp = reinterpret_cast<const char*>(g.zp + cb * BN);
+    const size_t s_row = size_t(N) * 2, z_row = size_t(N) * 4;
     for (int i = 0; i < nstages; ++i) {
-      if (!first_round) mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+      if (i >= g.ring) mbar_wait(bar_empty + 8 * slot, phase ^ 1);
       const uint32_t dst = stages + slot * g.stage_bytes;
       const uint32_t fb = bar_full + 8 * slot;
       const int qa = qa0 + 4 * i;
       const int grp0 = g.gshift >= 0 ? qa >> g.gshift : 0;
       const int ng = min(g.gps, g.ngroups - grp0);
-      mbar_expect_tx(fb, (g.dbg & 2 ? 0 : g.w_bytes) + (g.dbg & 4 ? 0 : ng * cols * 6));
-      if (!(g.dbg & 2)) tma_3d(dst, &tmw, 0, qa * 4, cb * nw, fb);
-      if (!(g.dbg & 4)) {
-        for (int j = 0; j < ng; ++j) {
-          bulk_g2s(dst + s_off + j * BN * 2, g.s + size_t(grp0 + j) * N + cb * BN, cols * 2, fb);
-          bulk_g2s(dst + z_off + j * BN * 4, g.zp + size_t(grp0 + j) * N + cb * BN, cols * 4, fb);
+      if (leader) {
+        mbar_expect_tx(fb, (g.dbg & 2 ? 0 : g.w_bytes) + (g.dbg & 4 ? 0 : ng * meta_bytes));
+        if (!(g.dbg & 2)) tma_3d(dst, &tmw, 0, qa * 4, cb * nw, fb);
+        if (!(g.dbg & 4)) {
+#pragma unroll 1
+          for (int j = 0; j < ng; ++j) {
+            bulk_g2s(dst + s_off + j * BN * 2, sp + size_t(grp0 + j) * s_row, cols * 2, fb);
+            bulk_g2s(dst + z_off + j * BN * 4, zp + size_t(grp0 + j) * z_row, cols * 4, fb);
+          }
         }
       }
       if (i == 0) STAMP(6);
       if (++slot == g.ring) {
         slot = 0;
         phase ^= 1;
-        first_round = false;
       }
     }
     STAMP(7);
@@ -539,6 +543,23 @@ __global__ void __launch_bounds__(32 * (2 * MAXNW + 1), 1) ring_gemv(const __gri
   STAMP(5);
 }
 
+// L2 prefetch of the head of a GEMV's weights: the first `rows` packed rows of each of the S K-slabs (contiguous, rows * 4N bytes each).
+// Launched with programmatic dependent launch BEFORE the GEMV it serves: it runs while the previous GEMV is still computing, and
+// only completes once that GEMV has (griddepcontrol.wait), so the stream order seen by the next kernel is unchanged.
+__global__ void __launch_bounds__(128) l2_prefetch(const uint32_t* wq, int K8, int N, int S, int rows) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const size_t slab_bytes = size_t(rows) * N * 4;
+  const int chunks_per_slab = int((slab_bytes + 4095) / 4096);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks_per_slab * S; c += gridDim.x * blockDim.x) {
+    const int r = c / chunks_per_slab, cc = c - r * chunks_per_slab;
+    const char* base = reinterpret_cast<const char*>(wq + size_t((long long)r * (K8 / 4) / S * 4) * N);
+    const size_t off = size_t(cc) * 4096;
+    const uint32_t bytes = uint32_t(min(size_t(4096), slab_bytes - off));
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(bytes) : "memory");
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------------------------------------
 // reference: out[m][n] = sum_k x[m][k] * fp16((q - z) * s), fp32 accumulation
 __global__ void ref_gemv(const uint32_t* wq, const __half* s, const int* zp, const __half* x, float* out, int M, int K, int N, int gs) {
@@ -616,6 +637,7 @@ static int g_sms = 148;
 static int g_ring_kb = 200;
 static int g_nw_override = 0, g_s_override = 0, g_ngrp_override = 0;
 static long long* g_trace = nullptr;
+static int g_pf_mb = 0;
 static int g_dbg = 0;
 
 // column-block width (consumer warps) and K slabs: as many CTAs as fit one wave of clusters
@@ -623,12 +645,13 @@ static void plan(int K, int N, int* nw_out, int* s_out) {
   const int cap[9] = {0, 148, 148, 0, 132, 0, 0, 0, 128};
   double best = -1;
   for (int nw = MAXNW; nw >= 4; --nw)
-    for (int S : {1, 2, 4}) {
+    for (int S : {1, 2, 4, 8}) {
+      if (S == 8 && !g_s_override) continue;
       if (g_nw_override && nw != g_nw_override) continue;
       if (g_s_override && S != g_s_override) continue;
       const int ncb = (N + 32 * nw - 1) / (32 * nw);
       const int ctas = ncb * S;
-      if ((ctas > cap[S] && !(g_nw_override && g_s_override)) || K / 32 / S < 4) continue;
+      if ((ctas > cap[S] && !(g_nw_override || g_s_override)) || K / 32 / S < 4) continue;
       const double eff = double(N) * S / (32 * nw);  // SMs' worth of evenly loaded CTAs
       if (eff > best + 1e-9) { best = eff; *nw_out = nw; *s_out = S; }
     }
@@ -666,6 +689,24 @@ static Geo make_geo(const Layer& L, int M, int gs, size_t* smem, dim3* grid) {
 }
 
 static void launch(const Layer& L, int M, int gs, bool pdl, cudaStream_t st) {
+  if (g_pf_mb > 0) {
+    const size_t total = size_t(L.K / 8) * L.N * 4;
+    const size_t want = std::min(total, size_t(g_pf_mb) << 20);
+    int rows = int(want / L.S / (size_t(L.N) * 4));
+    rows = std::min(rows, L.K / 8 / L.S);
+    if (rows > 0) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(148);
+      cfg.blockDim = dim3(128);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl ? 1 : 0;
+      CK(cudaLaunchKernelEx(&cfg, l2_prefetch, (const uint32_t*)L.wq, L.K / 8, L.N, L.S, rows));
+    }
+  }
   size_t smem;
   dim3 grid;
   Geo g = make_geo(L, M, gs, &smem, &grid);
@@ -702,6 +743,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--nw")) g_nw_override = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--s")) g_s_override = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--ngrp")) g_ngrp_override = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--pf")) g_pf_mb = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--sets")) nsets = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--dbg")) g_dbg = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--trace")) do_trace = true;
