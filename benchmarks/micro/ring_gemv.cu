@@ -297,32 +297,45 @@ __global__ void __launch_bounds__(32 * (2 * MAXNW + 1), 1) ring_gemv(const __gri
     const int cpr = nstages * 16;                 // chunks per row, counted from the aligned start qa0
     const int c_lo = (q_lo - qa0) * 4, c_hi = (q_hi - qa0) * 4;
     const int esh = 2 + mshift;                   // chunks per scale row = 1 << esh
-    for (int base = threadIdx.x & ~31; base < M * cpr; base += nthr) {
-      const int idx = base + lane;
-      const int m = idx / cpr, cc = idx - m * cpr;
-      const bool ok = idx < M * cpr && cc >= c_lo && cc < c_hi;
-      float sum = 0.f;
-      if (ok) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(g.x + size_t(m) * g.K + size_t(qa0) * 32) + cc);
-        uint4 o;
-        o.x = __byte_perm(v.x, v.z, 0x5410);
-        o.y = __byte_perm(v.y, v.w, 0x5410);
-        o.z = __byte_perm(v.x, v.z, 0x7632);
-        o.w = __byte_perm(v.y, v.w, 0x7632);
-        sts128(xs + m * g.x_pitch + (cc - c_lo) * 16, o);
-        const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+    constexpr int XU = 4;  // loads in flight per thread
+    for (int base0 = threadIdx.x & ~31; base0 < M * cpr; base0 += XU * nthr) {
+      uint4 v[XU];
+      int mm[XU], cv[XU];
+      bool ok[XU];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[k]));
-          sum += f.x + f.y;
-        }
+      for (int u = 0; u < XU; ++u) {
+        const int idx = base0 + u * nthr + lane;
+        mm[u] = idx / cpr;
+        cv[u] = idx - mm[u] * cpr;
+        ok[u] = idx < M * cpr && cv[u] >= c_lo && cv[u] < c_hi;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(g.x + size_t(mm[u]) * g.K + size_t(qa0) * 32) + cv[u]);
       }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      if (esh > 2) sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-      if (esh > 3) sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-      if (idx < M * cpr && (cc & ((1 << esh) - 1)) == 0)
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + ((cc >> esh) * 8 + m) * 4), "f"(sum) : "memory");
+#pragma unroll
+      for (int u = 0; u < XU; ++u) {
+        if (base0 + u * nthr >= M * cpr) break;  // (warp-uniform)
+        float sum = 0.f;
+        if (ok[u]) {
+          uint4 o;
+          o.x = __byte_perm(v[u].x, v[u].z, 0x5410);
+          o.y = __byte_perm(v[u].y, v[u].w, 0x5410);
+          o.z = __byte_perm(v[u].x, v[u].z, 0x7632);
+          o.w = __byte_perm(v[u].y, v[u].w, 0x7632);
+          sts128(xs + mm[u] * g.x_pitch + (cv[u] - c_lo) * 16, o);
+          const uint32_t r[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[k]));
+            sum += f.x + f.y;
+          }
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (esh > 2) sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        if (esh > 3) sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        if (base0 + u * nthr + lane < M * cpr && (cv[u] & ((1 << esh) - 1)) == 0)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + ((cv[u] >> esh) * 8 + mm[u]) * 4), "f"(sum) : "memory");
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
   }
