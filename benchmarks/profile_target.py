@@ -25,7 +25,6 @@ def main() -> None:
     ap.add_argument("--wtype", default="uint4")
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--stream-dbg", type=int, default=0, help="cb200_debug_set_stream_switches value (timing experiments)")
     args = ap.parse_args()
     k, n = SHAPES[args.shape]
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
@@ -34,7 +33,6 @@ def main() -> None:
     sets = [quant_utils.random_packed_weights(k, n, st, 128, dtype, "cuda", seed=i) for i in range(copies)]
     x = torch.randn((args.m, k), device="cuda", dtype=dtype)
     out = torch.empty((args.m, n), device="cuda", dtype=dtype)
-    _lib.load().cb200_debug_set_stream_switches(args.stream_dbg)
     for i in range(args.iters):
         s = sets[i % copies]
         mixed_precision_gemm(x, s[0], s[1], s[2], st.size_bits, st.bias, 128, out=out, variant=args.variant)

@@ -17,8 +17,8 @@ LIB_PATH = _PKG / ("libconch_b200_dbg.so" if os.environ.get("CB200_DEBUG_LIB") =
 # enums of include/conch_b200.h
 F16, BF16, F32 = 0, 1, 2
 ZP_NONE, ZP_I32, ZP_U8, ZP_ACT = 0, 1, 2, 3
-AUTO, DECODE_MMA, TC_SS, TC_TS, TC2_TS, DECODE_STREAM, DECODE_TCS = 0, 1, 2, 3, 4, 5, 6
-VARIANT_NAMES = {AUTO: "auto", DECODE_MMA: "decode_mma", TC_SS: "tc_ss", TC_TS: "tc_ts", TC2_TS: "tc2_ts", DECODE_STREAM: "decode_stream", DECODE_TCS: "decode_tcs"}
+AUTO, DECODE_MMA, TC_SS, TC_TS, TC2_TS, DECODE_STREAM = 0, 1, 2, 3, 4, 5
+VARIANT_NAMES = {AUTO: "auto", DECODE_MMA: "decode_mma", TC_SS: "tc_ss", TC_TS: "tc_ts", TC2_TS: "tc2_ts", DECODE_STREAM: "decode_stream"}
 ERR_ARG, ERR_SHAPE, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_DEVICE = -1, -2, -3, -4, -5
 WORKSPACE_COUNTER_BYTES = 65536
 
@@ -39,7 +39,6 @@ EXPORTS = (
     "cb200_set_pdl",
     "cb200_set_tc_cluster",
     "cb200_set_stream_tuning",
-    "cb200_debug_set_stream_switches",
     "cb200_debug_set_stream_trace",
 )
 
@@ -108,8 +107,6 @@ def load() -> ctypes.CDLL:
         lib.cb200_set_stream_tuning.argtypes = [c_int, c_int]
         lib.cb200_debug_set_stream_trace.restype = None
         lib.cb200_debug_set_stream_trace.argtypes = [c_void_p]
-        lib.cb200_debug_set_stream_switches.restype = None
-        lib.cb200_debug_set_stream_switches.argtypes = [c_int]
         lib.cb200_set_pdl.restype = None
         lib.cb200_set_pdl.argtypes = [c_int]
         _lib = lib

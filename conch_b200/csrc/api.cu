@@ -139,7 +139,6 @@ void cb200_set_tc_tuning(int m_tile, int split_k) { g_tc_tuning = {m_tile, split
 void cb200_set_tc_cluster(int ctas) { g_tc_cluster = (ctas == 1 || ctas == 2 || ctas == 4) ? ctas : 0; }
 void cb200_set_pdl(int enable) { g_decode_pdl = enable ? 1 : 0; }
 void cb200_set_stream_tuning(int ring_kb, int ctas) { g_stream_tuning = {ring_kb, ctas, g_stream_tuning.dbg}; }
-void cb200_debug_set_stream_switches(int switches) { g_stream_tuning.dbg = switches; }
 void cb200_debug_set_stream_trace(void* device_buffer) { g_stream_trace = reinterpret_cast<long long*>(device_buffer); }
 
 size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_size_bits, int variant) {
@@ -148,10 +147,8 @@ size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_
   const size_t a = decode_workspace_bytes(M, K, N, bits);
   const size_t b = tc_workspace_bytes(M, K, N);
   const size_t c = stream_workspace_bytes(M, K, N, bits);
-  const size_t d = tcs_workspace_bytes(M, K, N, bits);
   size_t need = a > b ? a : b;
-  need = c > need ? c : need;
-  return d > need ? d : need;
+  return c > need ? c : need;
 }
 
 int cb200_dequantize(const void* w_q_packed, const void* w_s, const void* w_zp, void* w_out, int64_t K, int64_t N,
@@ -263,14 +260,18 @@ int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* 
 
   int chosen = variant;
   if (chosen == CB200_AUTO) {
-    // regime split by MEASUREMENT (profiles/r02_decode_variants.log): HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile
-    // of x) on the register-window kernel; tcgen05 pipeline above.  The two streaming kernels (CB200_DECODE_STREAM,
-    // CB200_DECODE_TCS) are parity-tested opt-in variants: on a B200 their fine-grained producer / consumer handshakes cost
-    // more than the cross-kernel overlap they buy.
+    // regime split by MEASUREMENT (profiles/r02_*): HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x) on the
+    // streaming ring kernel where it has an operand format and a stage layout for the problem, else on round 1's
+    // register-window kernel (bf16 x int8, group sizes that straddle stages, completion flags); tcgen05 pipeline above.
     const bool decode = M <= 8;
-    chosen = (decode || !tc_supported(p, weight_size_bits)) ? CB200_DECODE_MMA : CB200_TC_TS;
+    if (decode || !tc_supported(p, weight_size_bits)) {
+      chosen = (decode && p.local_flag == nullptr && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM
+                                                                                                       : CB200_DECODE_MMA;
+    } else {
+      chosen = CB200_TC_TS;
+    }
   }
-  if (num_peers > 0 && chosen != CB200_DECODE_MMA && chosen != CB200_DECODE_STREAM && chosen != CB200_DECODE_TCS) {
+  if (num_peers > 0 && chosen != CB200_DECODE_MMA && chosen != CB200_DECODE_STREAM) {
     // the fused push lives in the decode kernels' (tiny) epilogue; big outputs are bandwidth-bound: all-gather them
     set_error("cb200_mpgemm_push: only the decode kernels (M <= 16) store to peers; use an all-gather for M=%lld", (long long)M);
     return CB200_ERR_UNSUPPORTED;
@@ -284,16 +285,10 @@ int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* 
     rc = launch_decode(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
   } else if (chosen == CB200_DECODE_STREAM) {
     if (!stream_supported(p, weight_size_bits, act_dtype)) {
-      set_error("the streaming decode kernel does not support this problem (bf16 x int8: use CB200_DECODE_MMA)");
+      set_error("the streaming decode kernel does not support this problem (bf16 x int8, or a group size that is neither 1, 2 nor a multiple of 4 quads of packed rows: use CB200_DECODE_MMA)");
       return CB200_ERR_UNSUPPORTED;
     }
     rc = launch_stream(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
-  } else if (chosen == CB200_DECODE_TCS) {
-    if (!tcs_supported(p, weight_size_bits, act_dtype)) {
-      set_error("the tcgen05 streaming decode kernel does not support this problem (bf16 x int8, or int4 with group_size %% 128 != 0)");
-      return CB200_ERR_UNSUPPORTED;
-    }
-    rc = launch_tcs(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
   } else if (chosen == CB200_TC_SS || chosen == CB200_TC_TS || chosen == CB200_TC2_TS) {
     if (!tc_supported(p, weight_size_bits)) {
       set_error("tcgen05 variant %d does not support this problem", chosen);

@@ -78,13 +78,10 @@ int launch_stream(const Problem& p, int bits, int act_dtype, void* ws, size_t ws
 size_t stream_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
 bool stream_supported(const Problem& p, int bits, int act_dtype);
 int launch_wait_flags(const uint32_t* flags, int count, uint32_t* expected, cudaStream_t stream);
-int launch_tcs(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
-size_t tcs_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
-bool tcs_supported(const Problem& p, int bits, int act_dtype);
 struct StreamTuning {
-  int ring_kb;   // shared memory the ring may use per CTA, in KiB (0 = heuristic)
-  int ctas;      // CTAs launched (0 = one per SM)
-  int dbg;       // debug switches, see StreamGeom::dbg (results are wrong when set: timing experiments only)
+  int ring_kb;   // shared memory the kernel may use per CTA, in KiB (0 = all of it)
+  int ctas;      // upper bound on the CTAs launched (0 = one per SM)
+  int dbg;       // unused
 };
 extern StreamTuning g_stream_tuning;
 extern long long* g_stream_trace;  // device buffer the next stream_kernel launches stamp (nullptr = off)

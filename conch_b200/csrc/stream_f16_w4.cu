@@ -2,5 +2,5 @@
 #include "stream_impl.cuh"
 
 namespace cb200 {
-CB200_STREAM_ENTRY(launch_stream_f16_w4) { return launch_stream_typed<__half, 4>(mw, mx, p, geo, ctas, smem, wsp, wsc, stream); }
+CB200_STREAM_ENTRY(launch_stream_f16_w4) { return launch_stream_typed<__half,4>(mw, p, geo, grid, smem, pdl, stream); }
 }  // namespace cb200

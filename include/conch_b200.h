@@ -59,11 +59,12 @@ enum cb200_variant {
   CB200_TC_SS = 2,        /* tcgen05: TMA -> smem dequant (K-major, 128B swizzle) -> UMMA (both operands smem), TMEM accumulators */
   CB200_TC_TS = 3,        /* tcgen05: TMA -> dequant straight into TMEM (W is the TMEM A operand), x tile from smem */
   CB200_TC2_TS = 4,       /* persistent tcgen05 kernel: m_tile 128, two TMEM accumulators, epilogue overlaps the next tile */
-  CB200_DECODE_STREAM = 5,/* opt-in, <= 16 rows per pass: persistent stream-K GEMV, TMA weight ring in shared memory, mma.sync dot, half an
-                             SM per kernel so that consecutive GEMVs overlap under programmatic dependent launch (bf16 x int8 excluded) */
-  CB200_DECODE_TCS = 6    /* opt-in, <= 32 rows per pass: persistent stream-K GEMV on tcgen05 -- TMA ring, nibbles masked into subnormal
-                             fp16 operands written straight into TMEM, per-scale-group fold from the TMEM accumulator (bf16 x int8 and
-                             int4 with group_size % 128 != 0 excluded).  Both are measured slower than CB200_DECODE_MMA: DESIGN.md 4.4 */
+  CB200_DECODE_STREAM = 5 /* <= 16 rows per pass (AUTO: M <= 8): warp-specialised streaming GEMV -- a producer warp keeps a ring of TMA weight
+                             tiles in shared memory full (it never waits for the stream order: under programmatic dependent launch
+                             the ring fills while the previous kernel drains), 12-16 consumer warps turn nibbles into subnormal fp16
+                             MMA operands, K is split over a thread-block cluster whose partial sums meet in distributed shared
+                             memory (no workspace, no atomics, deterministic).  bf16 x int8 and group sizes that straddle a
+                             16-packed-row stage are left to CB200_DECODE_MMA. */
 };
 
 enum cb200_status {
@@ -101,7 +102,7 @@ CB200_API int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_
  * process, to an [M, N] buffer of another GPU (CUDA IPC / symmetric memory): typically this rank's slot of every other
  * rank's gather buffer, so an N-sharded layer needs no separate all-gather.  The stores are plain P2P writes over NVLink,
  * visible to the peer once this kernel has completed; synchronising the ranks (one barrier per token, say) is the
- * caller's job.  Decode kernel only: AUTO picks it for M <= 8, variant = CB200_DECODE_MMA forces
+ * caller's job.  Decode kernels only: AUTO picks one for M <= 8, variant = CB200_DECODE_MMA / CB200_DECODE_STREAM forces
  * it for any M (16 rows per pass); any other choice returns CB200_ERR_UNSUPPORTED -- large outputs are bandwidth-bound and
  * belong to an all-gather. */
 CB200_API int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
@@ -154,15 +155,12 @@ CB200_API void cb200_set_tc_tuning(int m_tile, int split_k);
  * measured neutral). */
 CB200_API void cb200_set_tc_cluster(int ctas);
 
-/* Debug/tuning knobs of the streaming decode kernel (0 = heuristic): shared memory of the weight ring per CTA in KiB
- * (default 110: two kernels per SM), number of CTAs (default: one per SM).  Process-global, not thread-safe. */
+/* Debug/tuning knobs of the streaming decode kernel (0 = heuristic): shared memory per CTA in KiB (default: all of it),
+ * upper bound on the number of CTAs (default: one per SM).  Process-global, not thread-safe. */
 CB200_API void cb200_set_stream_tuning(int ring_kb, int ctas);
-/* Timing experiments only (results are WRONG when non-zero): 1 consumers skip the math, 2 no weight loads, 4 no x loads,
- * 8 no scale / zero-point loads; 16 (results stay correct): four 2-D weight TMAs per stage instead of one 3-D one.
- * Used by benchmarks/stream_anatomy.py to attribute time to the producer or the consumers. */
-CB200_API void cb200_debug_set_stream_switches(int switches);
 /* Timeline of the streaming decode kernel: when non-NULL, every following launch stamps %globaltimer at its milestones into
- * device_buffer[cta * 16 + slot] (int64; slots documented in benchmarks/stream_trace.py).  NULL switches it off. */
+ * device_buffer[cta * 8 + slot] (int64; slots documented in benchmarks/stream_trace.py; debug builds -DCB200_TC_TRACE only).
+ * NULL switches it off. */
 CB200_API void cb200_debug_set_stream_trace(void* device_buffer);
 
 /* Programmatic dependent launch for the decode kernels (default off).  When enabled, a decode kernel may start while the
