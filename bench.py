@@ -303,6 +303,7 @@ def run_gpu_arm(args) -> None:
 
     # ---- warm-up (eager), then capture one step into a CUDA graph ---------------------------------------------
     step(count=True)
+    decode_variant = lib.cb200_last_variant()  # the kernel family AUTO dispatched the step's GEMVs to
     for _ in range(max(0, args.warmup - 1)):
         step()
     barrier()
@@ -450,7 +451,7 @@ def run_gpu_arm(args) -> None:
                 "frac": per_gpu / peak,
                 "traffic": traffic,
                 "peak_source": peak_src,
-                "kernel": "cb200::decode_kernel<__half,4,1,4,CB200_ZP_I32,FUSED=true>",
+                "kernel": ("cb200::stream_kernel<__half,4,1>" if decode_variant == _lib.DECODE_STREAM else "cb200::decode_kernel<__half,4,1,4,CB200_ZP_I32,FUSED=true>") + " (" + _lib.VARIANT_NAMES[decode_variant] + ")",
                 "algorithmic_bytes_per_launch": algorithmic_bytes() / (LAYERS * len(PROJECTIONS)),
                 "avg_launch_us": ms_per_step * 1e3 / (LAYERS * len(PROJECTIONS)),
             },

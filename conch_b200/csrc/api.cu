@@ -262,10 +262,10 @@ int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* 
   if (chosen == CB200_AUTO) {
     // regime split by MEASUREMENT (profiles/r02_*): HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x) on the
     // streaming ring kernel where it has an operand format and a stage layout for the problem, else on round 1's
-    // register-window kernel (bf16 x int8, group sizes that straddle stages, completion flags); tcgen05 pipeline above.
+    // register-window kernel (bf16 x int8, group sizes that straddle stages); tcgen05 pipeline above.
     const bool decode = M <= 8;
     if (decode || !tc_supported(p, weight_size_bits)) {
-      chosen = (decode && p.local_flag == nullptr && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM
+      chosen = (decode && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM
                                                                                                        : CB200_DECODE_MMA;
     } else {
       chosen = CB200_TC_TS;
@@ -276,8 +276,8 @@ int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* 
     set_error("cb200_mpgemm_push: only the decode kernels (M <= 16) store to peers; use an all-gather for M=%lld", (long long)M);
     return CB200_ERR_UNSUPPORTED;
   }
-  if (p.local_flag != nullptr && (chosen != CB200_DECODE_MMA || M > 16)) {
-    set_error("cb200_mpgemm_push_signal: the completion flags are raised by the register-window decode kernel only (M <= 16 in one pass)");
+  if (p.local_flag != nullptr && ((chosen != CB200_DECODE_MMA && chosen != CB200_DECODE_STREAM) || M > 16)) {
+    set_error("cb200_mpgemm_push_signal: the completion flags are raised by the decode kernels only (M <= 16 in one pass)");
     return CB200_ERR_UNSUPPORTED;
   }
   int launches = 0;

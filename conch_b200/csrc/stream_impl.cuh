@@ -33,6 +33,7 @@ struct StreamGeom {
   int x_bytes;      // staged x slab
   int red_bytes;    // cluster reduction buffers + the group sums of x (at its end)
   int xsum_bytes;
+  unsigned int* done;  // cb200_mpgemm_push_signal: self-resetting counter of finished 32-column slices (workspace), else unused
   long long* trace; // debug builds: [CTA][8] globaltimer stamps
 };
 
@@ -639,6 +640,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
           store_out4_all(p, size_t(m) * N + col, r);
         }
       }
+    push_signal_block_done(p, geo.done, unsigned(N / 32), lane);  // (no-op unless completion flags were asked for)
   }
   RING_STAMP(5);
 }

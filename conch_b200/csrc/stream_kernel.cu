@@ -117,7 +117,8 @@ static StreamPlan stream_plan(int mrows, int K, int N, int bits, int g, int zp_k
   return pl;
 }
 
-size_t stream_workspace_bytes(int64_t, int64_t, int64_t, int) { return 0; }  // partial sums travel through distributed shared memory
+// partial sums travel through distributed shared memory; only the completion-flag counter of cb200_mpgemm_push_signal lives there
+size_t stream_workspace_bytes(int64_t, int64_t, int64_t, int) { return CB200_WORKSPACE_COUNTER_BYTES; }
 
 // packed W [K/pf, N] int32 as a 3-D tensor {32 columns, K/pf rows, N/32 column slices}, strides {N*4, 128}, box {32, 16, nw}: the
 // smem image is nw [16 rows x 128 B] blocks, each 128-byte swizzled on its own row index.  Encoding costs a few microseconds of
@@ -160,7 +161,11 @@ static int stream_tmap(const Problem& p, int pf, int nw, const CUtensorMap** out
   return 0;
 }
 
-int launch_stream(const Problem& p_in, int bits, int act_dtype, void*, size_t, cudaStream_t stream, int* launches) {
+int launch_stream(const Problem& p_in, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches) {
+  if (p_in.local_flag != nullptr && (ws == nullptr || ws_bytes < size_t(CB200_WORKSPACE_COUNTER_BYTES))) {
+    set_error("cb200_mpgemm_push_signal needs the %d-byte counter area of the workspace", CB200_WORKSPACE_COUNTER_BYTES);
+    return CB200_ERR_WORKSPACE;
+  }
   if (size_t(p_in.K / p_in.g) * p_in.N >= (size_t(1) << 31)) {
     set_error("scale matrix too large");
     return CB200_ERR_SHAPE;
@@ -199,6 +204,7 @@ int launch_stream(const Problem& p_in, int bits, int act_dtype, void*, size_t, c
     geo.x_bytes = pl.x_bytes;
     geo.red_bytes = pl.red_bytes;
     geo.xsum_bytes = pl.xsum_bytes;
+    geo.done = ws ? reinterpret_cast<unsigned int*>(ws) + (CB200_WORKSPACE_COUNTER_BYTES / 4 - 1) : nullptr;
     geo.trace = g_stream_trace;
     const bool pdl = g_decode_pdl != 0;
     int rc;

@@ -118,7 +118,7 @@ CB200_API int cb200_mpgemm_push(const void* x, const void* w_q_packed, const voi
  * zero-initialised).  A consumer on any GPU that needs the gathered output waits until all `world` counters of ITS array have
  * reached the number of signalled GEMVs so far: cb200_wait_flags keeps that number in `*expected` (device memory, zero-
  * initialised, advanced by the wait itself), so a signalled GEMV followed by ONE wait on every rank is safe to capture in a
- * CUDA graph and replay.  Register-window decode kernel only (AUTO: M <= 8; M <= 16 with variant = CB200_DECODE_MMA).
+ * CUDA graph and replay.  Decode kernels only (AUTO: M <= 8; M <= 16 with variant = CB200_DECODE_MMA / CB200_DECODE_STREAM).
  * local_flag == NULL: plain cb200_mpgemm_push. */
 CB200_API int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
                  int64_t M, int64_t K, int64_t N,

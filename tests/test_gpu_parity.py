@@ -423,8 +423,8 @@ def test_push_signal_counts_and_wait_is_replay_safe():
             g.replay()
     torch.cuda.synchronize()
     assert flags[:3].tolist() == [7, 7, 7] and int(flags[8]) == 7
-    with pytest.raises(NotImplementedError):  # the flags are raised by the register-window decode kernel only
-        mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, out=out, variant=_lib.DECODE_STREAM, peer_out_ptrs=[peers[0].data_ptr()], signal=sig)
+    with pytest.raises(NotImplementedError):  # the flags are raised by the decode kernels only
+        mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, out=out, variant=_lib.TC_TS, peer_out_ptrs=[peers[0].data_ptr()], signal=sig)
 
 
 def test_push_epilogue_is_decode_only():
