@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
     const uint2 sv = lds64(st + lane_s + mrow * (BN * 2));
     A s4[4];
     *reinterpret_cast<uint2*>(s4) = sv;
-    float z[4] = {zscalar, zscalar, zscalar, zscalar};
+    float z[4];
     if (zes == 4) {
       const uint4 zv = lds128(st + lane_z + mrow * (BN * 4));
       z[0] = float(int(zv.x)); z[1] = float(int(zv.y)); z[2] = float(int(zv.z)); z[3] = float(int(zv.w));
@@ -421,6 +421,9 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
       *reinterpret_cast<uint2*>(z4) = zv;
 #pragma unroll
       for (int c = 0; c < 4; ++c) z[c] = ActOps<A>::to_float(z4[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) z[c] = zscalar;
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -479,8 +482,8 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
   auto advance = [&]() {
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
-    slot += NGRP;
-    while (slot >= geo.ring) {
+    slot += NGRP;  // (the ring is a multiple of the number of groups: at most one wrap)
+    if (slot >= geo.ring) {
       slot -= geo.ring;
       phase ^= 1;
     }

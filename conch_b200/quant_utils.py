@@ -51,10 +51,12 @@ def quantize_weights(
     quant_type: ScalarType,
     group_size: int | None,
     zero_points: bool = False,
+    ref_zero_points_after_scales: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor | None]:
     """Min/max group quantiser.  Returns (w_ref, w_q, w_s, w_zp) like the reference helper
     (conch/third_party/vllm/quant_utils.py:14-101): w_ref [K,N] w.dtype, w_q [K,N] int32 stored values
-    (bias added), w_s [K/g,N] w.dtype, w_zp [K/g,N] int32 or None."""
+    (bias added), w_s [K/g,N] w.dtype, w_zp [K/g,N] int32 or None.  ref_zero_points_after_scales computes w_ref as
+    q * s - zp * s (two roundings, reference :71-74) instead of (q - zp) * s."""
     if not w.is_floating_point() or w.dim() != 2:
         raise ValueError("w must be a 2-D floating point tensor")
     size_k, size_n = w.shape
@@ -69,7 +71,10 @@ def quantize_weights(
         w_s = (w_max - w_min).clamp(min=1e-5) / q_hi
         w_zp = torch.round(torch.abs(w_min / w_s)).clamp(q_lo, q_hi).to(torch.int32)
         w_q = (torch.round(groups / w_s).to(torch.int32) + w_zp).clamp(q_lo, q_hi)
-        w_ref = (w_q - w_zp).to(w.dtype) * w_s
+        if ref_zero_points_after_scales:
+            w_ref = w_q.to(w.dtype) * w_s - w_zp.to(w.dtype) * w_s
+        else:
+            w_ref = (w_q - w_zp).to(w.dtype) * w_s
     else:
         hi_div = float(q_hi) if q_hi != 0 else float("inf")
         lo_div = float(q_lo) if q_lo != 0 else float("inf")

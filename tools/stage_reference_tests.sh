@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+# Stage the reference's OWN test of the hot path next to the installed reference (baseline/, git-ignored, shipped to the GPU box
+# by gpurun) so that it can run UNMODIFIED against the conch -> conch_b200 shim:
+#     tools/stage_reference_tests.sh && gpurun -- 'PYTHONPATH=shim:. python -m pytest baseline/_ref_tests -q'
+# Nothing from /root/reference is copied into the tracked tree.
+set -euo pipefail
+ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+REF="${1:-/root/reference}"
+mkdir -p "$ROOT/baseline/_ref_tests"
+cp "$REF/tests/mixed_precision_gemm_test.py" "$ROOT/baseline/_ref_tests/"
+echo "staged $(ls "$ROOT/baseline/_ref_tests")"
