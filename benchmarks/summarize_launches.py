@@ -1,4 +1,5 @@
-"""profiles/traffic.json from the ncu launch list of bench.py (gpu__time_duration + dram bytes per decode_kernel launch).
+"""profiles/traffic.json from the ncu launch list of bench.py (gpu__time_duration + dram bytes per decode-regime kernel launch:
+cb200::stream_kernel, or cb200::decode_kernel where AUTO falls back to it).
 
     python benchmarks/summarize_launches.py profiles/r01_bench_launches.csv profiles/traffic.json
 """
@@ -14,7 +15,7 @@ def main() -> None:
     with open(src) as f:
         lines = [ln for ln in f if not ln.startswith("==")]
     for r in csv.DictReader(lines):
-        if "decode_kernel" not in r["Kernel Name"]:
+        if "decode_kernel" not in r["Kernel Name"] and "stream_kernel" not in r["Kernel Name"]:
             continue
         per[(int(r["ID"]), r["Grid Size"])][r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
     groups = collections.defaultdict(list)
@@ -32,7 +33,7 @@ def main() -> None:
     out = {
         "decode_kernel_dram_bytes_per_launch": tot_bytes / max(tot_n, 1),
         "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-        "-k regex:decode_kernel on bench.py --steps 2 --warmup 1 (" + src + "), averaged over all decode_kernel launches",
+        "-k regex:stream_kernel|decode_kernel on bench.py --steps 2 --warmup 1 (" + src + "), averaged over all decode-regime launches",
         "per_shape": shapes,
     }
     with open(dst, "w") as f:
