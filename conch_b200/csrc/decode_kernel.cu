@@ -77,17 +77,18 @@ struct DecodePlan {
 };
 
 // Every knob is overridable through cb200_set_decode_tuning(warps_n -> 1: per-weight dequant before the MMA (W bits
-// identical to the reference's w_ref), 2 (default, measured 5-10% faster): fused magic-number operands; warps_k -> CTAs
-// per SM assumed resident;
-// split_k -> forced split count S (rounded down to a legal divisor); vec_words unused).
-static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g) {
+// identical to the reference's w_ref), 2: fused magic-number operands (measured 5-10% faster), 0: fused except for
+// fp16 x int4 (`exact_default`), whose fused form pre-multiplies half of the activations by 1/16 IN FP16 and so loses bits
+// for |x| < 2^-10 -- ADVICE r1; that format's fast path is the streaming kernel, which scales an accumulator instead;
+// warps_k -> CTAs per SM assumed resident; split_k -> forced split count S (rounded down to a legal divisor); vec_words unused).
+static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g, bool exact_default = false) {
   DecodePlan pl;
   const int step_k = 4 * (32 / bits);
   pl.u = (g % (4 * step_k) == 0) ? 4 : 2;
   const int B = K / (pl.u * step_k);  // batches per column block
   pl.bpg = g / (pl.u * step_k);
   pl.col_blocks = N / 32;
-  pl.fused = g_decode_tuning.warps_n != 1;
+  pl.fused = g_decode_tuning.warps_n == 2 || (g_decode_tuning.warps_n == 0 && !exact_default);
   // __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   pl.ctas_per_sm = pick(g_decode_tuning.warps_k, mrows > 8 ? 3 : (pl.fused ? 4 : 5));
   const int by_regs = pl.ctas_per_sm;
@@ -158,13 +159,17 @@ size_t decode_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits) {
   for (int rows : {int(M < 16 ? M : 16), int(M > 16 ? ((M - 1) % 16) + 1 : (M < 16 ? M : 16))}) {
     for (int64_t g = 64; g <= K; g *= 2) {
       if (K % g) continue;
-      const DecodePlan pl = decode_plan(rows, int(K), int(N), bits, int(g));
-      const size_t b = pl.splits > 1 ? size_t(pl.total_warps) * rows * 32 * sizeof(float) : 0;
+      for (bool exact : {false, true}) {
+        const DecodePlan pl = decode_plan(rows, int(K), int(N), bits, int(g), exact);
+        const size_t b = pl.splits > 1 ? size_t(pl.total_warps) * rows * 32 * sizeof(float) : 0;
+        need = b > need ? b : need;
+      }
+    }
+    for (bool exact : {false, true}) {
+      const DecodePlan pk = decode_plan(rows, int(K), int(N), bits, int(K), exact);
+      const size_t b = pk.splits > 1 ? size_t(pk.total_warps) * rows * 32 * sizeof(float) : 0;
       need = b > need ? b : need;
     }
-    const DecodePlan pk = decode_plan(rows, int(K), int(N), bits, int(K));
-    const size_t b = pk.splits > 1 ? size_t(pk.total_warps) * rows * 32 * sizeof(float) : 0;
-    need = b > need ? b : need;
   }
   return size_t(CB200_WORKSPACE_COUNTER_BYTES) + need;
 }
@@ -182,7 +187,7 @@ int launch_decode(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     }
     p.M = mrows;
 
-    const DecodePlan pl = decode_plan(mrows, p.K, p.N, bits, p.g);
+    const DecodePlan pl = decode_plan(mrows, p.K, p.N, bits, p.g, act_dtype == CB200_F16 && bits == 4);
     const size_t need =
         size_t(CB200_WORKSPACE_COUNTER_BYTES) + (pl.splits > 1 ? size_t(pl.total_warps) * mrows * 32 * sizeof(float) : 0);
     if (pl.splits > 1 && (ws == nullptr || ws_bytes < need)) {
