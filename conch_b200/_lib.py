@@ -28,6 +28,7 @@ EXPORTS = (
     "cb200_last_error",
     "cb200_mpgemm_workspace_bytes",
     "cb200_mpgemm",
+    "cb200_mpgemm_bias",
     "cb200_mpgemm_push",
     "cb200_mpgemm_push_signal",
     "cb200_wait_flags",
@@ -84,6 +85,8 @@ def load() -> ctypes.CDLL:
             c_void_p, c_size_t,  # workspace
             c_int, c_void_p,  # variant, stream
         ]  # fmt: skip
+        lib.cb200_mpgemm_bias.restype = c_int
+        lib.cb200_mpgemm_bias.argtypes = lib.cb200_mpgemm.argtypes[:4] + [c_void_p] + lib.cb200_mpgemm.argtypes[4:]  # ..., w_zp, bias, out, ...
         lib.cb200_mpgemm_push.restype = c_int
         lib.cb200_mpgemm_push.argtypes = lib.cb200_mpgemm.argtypes + [ctypes.POINTER(c_void_p), c_int]  # peer_out, num_peers
         lib.cb200_mpgemm_push_signal.restype = c_int

@@ -201,10 +201,12 @@ int cb200_wait_flags(const void* flags, int count, void* expected, void* stream)
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
-int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M,
-                             int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
-                             int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
-                             void* stream, void* const* peer_out, int num_peers, void* const* peer_flags, void* local_flag) {
+}  // extern "C"
+
+static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M, int64_t K,
+                      int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype, int out_dtype,
+                      int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant, void* stream,
+                      void* const* peer_out, int num_peers, void* const* peer_flags, void* local_flag, const void* bias) {
   tls_last_variant = 0;
   tls_last_launches = 0;
   int rc = check_device();
@@ -230,6 +232,11 @@ int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* 
   p.zp_kind = zp_kind;
   p.zp_scalar = zp_is_scalar;
   p.out_dtype = out_dtype;
+  p.out_bias = bias;
+  if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & (out_dtype == CB200_F32 ? 3u : 1u))) {
+    set_error("bias is not aligned to its element size");
+    return CB200_ERR_ARG;
+  }
   if (num_peers < 0 || num_peers > CB200_MAX_PEERS || (num_peers > 0 && !peer_out)) {
     set_error("num_peers=%d out of range (0..%d)", num_peers, CB200_MAX_PEERS);
     return CB200_ERR_ARG;
@@ -306,6 +313,24 @@ int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* 
   tls_last_variant = chosen;
   tls_last_launches = launches;
   return rc;
+}
+
+extern "C" {
+
+int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M,
+                             int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
+                             int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
+                             void* stream, void* const* peer_out, int num_peers, void* const* peer_flags, void* local_flag) {
+  return run_mpgemm(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, weight_bias, group_size, act_dtype, out_dtype, zp_kind,
+                    zp_is_scalar, workspace, workspace_bytes, variant, stream, peer_out, num_peers, peer_flags, local_flag, nullptr);
+}
+
+int cb200_mpgemm_bias(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, const void* bias, void* out,
+                      int64_t M, int64_t K, int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype,
+                      int out_dtype, int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant,
+                      void* stream) {
+  return run_mpgemm(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, weight_bias, group_size, act_dtype, out_dtype, zp_kind,
+                    zp_is_scalar, workspace, workspace_bytes, variant, stream, nullptr, 0, nullptr, nullptr, bias);
 }
 
 }  // extern "C"

@@ -33,7 +33,16 @@ struct Problem {
   // local_flag are incremented by one: per-GEMM visibility without a cross-GPU barrier, safe under CUDA-graph replay
   uint32_t* peer_flag[CB200_MAX_PEERS];
   uint32_t* local_flag;
+  const void* out_bias;  // cb200_mpgemm_bias: [N] in the OUTPUT dtype, added to the fp32 sum before the one rounding (or null)
 };
+
+// bias[n] as fp32 (0 when there is none): every kernel adds it where it forms the final fp32 value of out[m, n]
+__device__ __forceinline__ float bias_at(const Problem& p, int n) {
+  if (p.out_bias == nullptr) return 0.f;
+  if (p.out_dtype == CB200_F16) return __half2float(reinterpret_cast<const __half*>(p.out_bias)[n]);
+  if (p.out_dtype == CB200_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.out_bias)[n]);
+  return reinterpret_cast<const float*>(p.out_bias)[n];
+}
 
 // Called by a warp that has finished (stored and pushed) one 32-column block of a cb200_mpgemm_push_signal GEMV: system-scope
 // fence, count the block, and -- as the last block of the grid -- raise the flags.  `done` is a self-resetting counter.

@@ -448,13 +448,14 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
       for (int mt = 0; mt < MT; ++mt) {
         const int m = mt * 8 + 2 * tig;
         const int n = col + 2 * t;
+        const float b0 = bias_at(p, n), b1 = bias_at(p, n + 1);
         if (m < M) {
-          store_out_all<A>(p, size_t(m) * N + n, acc[t][mt][0]);
-          store_out_all<A>(p, size_t(m) * N + n + 1, acc[t][mt][2]);
+          store_out_all<A>(p, size_t(m) * N + n, acc[t][mt][0] + b0);
+          store_out_all<A>(p, size_t(m) * N + n + 1, acc[t][mt][2] + b1);
         }
         if (m + 1 < M) {
-          store_out_all<A>(p, size_t(m + 1) * N + n, acc[t][mt][1]);
-          store_out_all<A>(p, size_t(m + 1) * N + n + 1, acc[t][mt][3]);
+          store_out_all<A>(p, size_t(m + 1) * N + n, acc[t][mt][1] + b0);
+          store_out_all<A>(p, size_t(m + 1) * N + n + 1, acc[t][mt][3] + b1);
         }
       }
     push_signal_block_done(p, ws_counter + (CB200_WORKSPACE_COUNTER_BYTES / 4 - 1), unsigned(C), lane);
@@ -496,6 +497,11 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
         v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
       }
+      if (p.out_bias != nullptr) {
+        const int n = cb * CW + lc;
+        v0.x += bias_at(p, n); v0.y += bias_at(p, n + 1); v0.z += bias_at(p, n + 2); v0.w += bias_at(p, n + 3);
+        v1.x += bias_at(p, n + 4); v1.y += bias_at(p, n + 5); v1.z += bias_at(p, n + 6); v1.w += bias_at(p, n + 7);
+      }
       store_out4_all(p, size_t(m) * N + cb * CW + lc, v0);
       store_out4_all(p, size_t(m) * N + cb * CW + lc + 4, v1);
     }
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
       float v = 0.f;
       for (int s = 0; s < S; ++s) v += __ldcg(base + size_t(s) * (M * CW) + e);
       const int m = e / CW, lc = e - m * CW;
-      store_out_all<A>(p, size_t(m) * N + cb * CW + lc, v);
+      store_out_all<A>(p, size_t(m) * N + cb * CW + lc, v + bias_at(p, cb * CW + lc));
     }
   }
   if (lane == 0) ws_counter[cb] = 0u;  // leave the counter clean for the next launch

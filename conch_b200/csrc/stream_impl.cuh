@@ -640,6 +640,9 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
             const float4 v = lds128f(recv + ((wslot * nsrc + src) * M + m) * 128 + ch * 16);
             r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
           }
+          if (p.out_bias != nullptr) {
+            r.x += bias_at(p, col); r.y += bias_at(p, col + 1); r.z += bias_at(p, col + 2); r.w += bias_at(p, col + 3);
+          }
           store_out4_all(p, size_t(m) * N + col, r);
         }
       }

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           if (split) {
             __stcg(part + (col0 + c) * Cfg::NTILE + nl, v);  // tile-local [m][n]: 128 contiguous bytes per warp store
           } else {
-            store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, v);
+            store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, v + bias_at(p, n));
           }
         }
       }
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1)
 #pragma unroll
         for (int cidx = 0; cidx < 32; ++cidx) {
           const int m = m0 + col0 + cidx;
-          if (m < p.M && n_ok) store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, __uint_as_float(r[cidx]));
+          if (m < p.M && n_ok) store_out<A>(p.out, p.out_dtype, size_t(m) * p.N + n, __uint_as_float(r[cidx]) + bias_at(p, n));
         }
       }
       tc_fence_before();
@@ -739,10 +739,10 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, Problem p, 
     const int n = (tile % n_tiles) * 128 + (rem & 31) * 4;
     if (m < p.M && n < p.N) {  // N % 64 == 0: a group of four columns is inside or outside as a whole
       const size_t o = size_t(m) * p.N + n;
-      store_out<float>(p.out, p.out_dtype, o + 0, v.x);
-      store_out<float>(p.out, p.out_dtype, o + 1, v.y);
-      store_out<float>(p.out, p.out_dtype, o + 2, v.z);
-      store_out<float>(p.out, p.out_dtype, o + 3, v.w);
+      store_out<float>(p.out, p.out_dtype, o + 0, v.x + bias_at(p, n));
+      store_out<float>(p.out, p.out_dtype, o + 1, v.y + bias_at(p, n + 1));
+      store_out<float>(p.out, p.out_dtype, o + 2, v.z + bias_at(p, n + 2));
+      store_out<float>(p.out, p.out_dtype, o + 3, v.w + bias_at(p, n + 3));
     }
   }
 }

@@ -105,8 +105,9 @@ def mixed_precision_gemm_launcher(
     variant: int = _lib.AUTO,
     peer_out_ptrs: Sequence[int] | None = None,
     signal: tuple[Sequence[int], int] | None = None,
+    bias: torch.Tensor | None = None,
 ) -> None:
-    """Enqueue out = x @ dequant(W) on the current CUDA stream.  Never synchronises.
+    """Enqueue out = x @ dequant(W) (+ bias) on the current CUDA stream.  Never synchronises.
 
     Counterpart of the reference launcher (conch/kernels/quantization/gemm.py:482-545): same argument order.
     `peer_out_ptrs` (multi-GPU, decode regime): device pointers of other GPUs' [M, N] buffers the kernel's epilogue also
@@ -145,6 +146,13 @@ def mixed_precision_gemm_launcher(
         stream,
     )  # fmt: skip
     entry = lib.cb200_mpgemm
+    ws_at = 15  # position of the workspace pointer in `args`
+    if bias is not None:
+        if peer_out_ptrs or signal is not None:
+            raise NotImplementedError("bias and the multi-GPU push epilogue cannot be combined")
+        entry = lib.cb200_mpgemm_bias  # (..., w_zp, bias, out, ...)
+        args = args[:4] + (bias.data_ptr(),) + args[4:]
+        ws_at = 16
     if peer_out_ptrs or signal is not None:
         peers = list(peer_out_ptrs or ())
         entry = lib.cb200_mpgemm_push
@@ -162,7 +170,7 @@ def mixed_precision_gemm_launcher(
     if rc == _lib.ERR_WORKSPACE:  # stale cached size (a tuning knob changed the plan): ask again, grow, retry once
         need = _need_cache[key] = lib.cb200_mpgemm_workspace_bytes(m, k, n, metadata.weight_size_bits, variant)
         ws = _workspace(device, stream, need)
-        args = args[:15] + (ws.data_ptr(), ws.numel()) + args[17:]
+        args = args[:ws_at] + (ws.data_ptr(), ws.numel()) + args[ws_at + 2 :]
         with torch.cuda.device(device):
             rc = entry(*args)
     _lib.raise_for_status(rc)

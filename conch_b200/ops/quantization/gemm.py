@@ -181,13 +181,17 @@ def mixed_precision_gemm(
     out: torch.Tensor | None = None,
     peer_out_ptrs: Sequence[int] | None = None,
     signal: tuple[Sequence[int], int] | None = None,
+    bias: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """Mixed precision GEMM: `x[M,K] @ dequant(w_q_packed[K/pf,N], w_s, w_zp) -> [M,N]`.
 
-    Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus three optional keywords:
+    Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus optional keywords:
     `variant` forces a kernel family (debug / benchmarking), `out` reuses a caller-owned output buffer, `peer_out_ptrs`
-    (multi-GPU, decode regime: M <= 8) lists peer-GPU buffers the kernel also stores the result to, and `signal` = (peer flag
-    pointers, local flag pointer) makes it bump completion counters on every GPU afterwards (conch_b200/sharded.py).
+    (multi-GPU, decode regime: M <= 8) lists peer-GPU buffers the kernel also stores the result to, `signal` = (peer flag
+    pointers, local flag pointer) makes it bump completion counters on every GPU afterwards (conch_b200/sharded.py), and
+    `bias` ([N], output dtype) is added in the kernels' epilogue -- to the fp32 sum, before the one rounding -- instead of by
+    the separate `output.add_(bias)` kernel a caller of the reference op runs (the reference's sibling op does exactly that,
+    conch/ops/quantization/gemm.py:249-250).
     """
     _require_device(x, w_q_packed, w_s, w_zp)
     metadata = create_mixed_precision_metadata(
@@ -199,14 +203,79 @@ def mixed_precision_gemm(
         # the reference honours arbitrary strides (gemm.py:518-525); the CUDA kernels want dense row-major
         x, w_q_packed, w_s = x.contiguous(), w_q_packed.contiguous(), w_s.contiguous()
         w_zp = None if w_zp is None else w_zp.contiguous()
+    # the kernels read with 16-byte vectors / TMA: a dense view that starts at an odd element of a bigger buffer is copied
+    # (the reference's Triton kernel accepts it as is)
+    if x.data_ptr() % 16:
+        x = x.clone()
+    if w_q_packed.data_ptr() % 16 or w_s.data_ptr() % 16 or (w_zp is not None and w_zp.numel() > 1 and w_zp.data_ptr() % 16):
+        w_q_packed, w_s = _dense_aligned(w_q_packed), _dense_aligned(w_s)
+        w_zp = None if w_zp is None else _dense_aligned(w_zp)
     if out is None:
         out = torch.empty((metadata.m_dim, metadata.n_dim), device=x.device, dtype=metadata.output_dtype)
     elif tuple(out.shape) != (metadata.m_dim, metadata.n_dim) or out.dtype != metadata.output_dtype or not out.is_contiguous():
         raise ValueError("`out` must be a contiguous [M, N] tensor of the output dtype")
+    if bias is not None:
+        if tuple(bias.shape) != (metadata.n_dim,) or bias.dtype != metadata.output_dtype or bias.device != x.device:
+            raise ValueError(f"`bias` must be a [{metadata.n_dim}] tensor of the output dtype {metadata.output_dtype} on {x.device}")
+        bias = bias.contiguous()
     if metadata.m_dim == 0:
         return out
-    mixed_precision_gemm_launcher(out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal)
+    mixed_precision_gemm_launcher(
+        out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, bias=bias
+    )
     return out
+
+
+class PreparedWeights:
+    """One layer's quantised weights, prepared ONCE for repeated calls (the vLLM-style caller).
+
+    The stateless op re-validates and re-derives everything per call and streams whatever zero-point dtype the quantiser
+    produced.  Preparation
+      * narrows per-group integer zero-points to uint8 (the reference quantiser emits int32, i.e. 4 bytes per group and
+        column where 4 or 8 bits carry the information: -3 bytes per 64 packed int4 bytes, 4.6 % less HBM traffic per GEMV),
+      * makes every tensor dense, 16-byte aligned and resident on one device,
+      * resolves the metadata (shapes, group size, dtypes) once,
+    and `__call__(x, bias=None, out=None)` runs the same kernels as `mixed_precision_gemm` with the bias fused into their
+    epilogue.  Results are bit-identical to the stateless op on the same inputs (the kernels read uint8 or int32 zero-points
+    through the same arithmetic)."""
+
+    def __init__(self, w_q_packed: torch.Tensor, w_s: torch.Tensor, w_zp: torch.Tensor | None, weight_size_bits: int,
+                 weight_bias: int, group_size: int) -> None:  # fmt: skip
+        _require_device(w_q_packed, w_s, w_zp)
+        if weight_size_bits not in (4, 8):
+            raise NotImplementedError(f"weight_size_bits={weight_size_bits}")
+        self.weight_size_bits, self.weight_bias = weight_size_bits, weight_bias
+        pf = 32 // weight_size_bits
+        self.k_dim, self.n_dim = w_q_packed.shape[0] * pf, w_q_packed.shape[1]
+        self.group_size = self.k_dim if group_size == -1 else group_size
+        if tuple(w_s.shape) != (self.k_dim // self.group_size, self.n_dim):
+            raise ValueError(f"Invalid w_s shape {tuple(w_s.shape)}")
+        self.w_q_packed = _dense_aligned(w_q_packed)
+        self.w_s = _dense_aligned(w_s)
+        if w_zp is not None and w_zp.numel() > 1 and w_zp.dtype in (torch.int32, torch.int64, torch.int16):
+            lo, hi = int(w_zp.min()), int(w_zp.max())
+            if lo < 0 or hi > 255:
+                raise ValueError(f"zero-points outside [0, 255] ({lo}..{hi}) cannot be narrowed to uint8")
+            w_zp = w_zp.to(torch.uint8)
+        self.w_zp = None if w_zp is None else _dense_aligned(w_zp)
+
+    def __call__(self, x: torch.Tensor, bias: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                 output_dtype: torch.dtype | None = None, variant: int = _lib.AUTO) -> torch.Tensor:  # fmt: skip
+        return mixed_precision_gemm(
+            x, self.w_q_packed, self.w_s, self.w_zp, self.weight_size_bits, self.weight_bias, self.group_size,
+            output_dtype=output_dtype, out=out, bias=bias, variant=variant,
+        )  # fmt: skip
+
+
+def _dense_aligned(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
+def prepare_weights(w_q_packed: torch.Tensor, w_s: torch.Tensor, w_zp: torch.Tensor | None, weight_size_bits: int,
+                    weight_bias: int, group_size: int) -> PreparedWeights:  # fmt: skip
+    """Prepare one layer's weights for repeated `mixed_precision_gemm` calls; see PreparedWeights."""
+    return PreparedWeights(w_q_packed, w_s, w_zp, weight_size_bits, weight_bias, group_size)
 
 
 def dequantize_weights(

@@ -97,6 +97,17 @@ CB200_API int cb200_mpgemm(const void* x, const void* w_q_packed, const void* w_
                  void* workspace, size_t workspace_bytes,
                  int variant, void* stream);
 
+/* cb200_mpgemm with a fused bias: out[m, n] = cast(sum_k x[m,k] W[k,n] + bias[n]), bias [N] in the OUTPUT dtype, added to the
+ * fp32 sum before the single rounding (bias == NULL: plain cb200_mpgemm).
+ * Replaces: the `output.add_(bias)` a caller of the reference op runs as a second kernel after mixed_precision_gemm_launcher
+ * (the reference's own sibling op does exactly that: conch/ops/quantization/gemm.py:249-250). */
+CB200_API int cb200_mpgemm_bias(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, const void* bias, void* out,
+                 int64_t M, int64_t K, int64_t N,
+                 int weight_size_bits, int weight_bias, int64_t group_size,
+                 int act_dtype, int out_dtype, int zp_kind, int zp_is_scalar,
+                 void* workspace, size_t workspace_bytes,
+                 int variant, void* stream);
+
 /* Multi-GPU epilogue (no counterpart in the reference, which has no distributed code): cb200_mpgemm whose
  * kernel ALSO stores the result into `num_peers` (<= 7) peer buffers -- peer_out[i] is a device pointer, valid in this
  * process, to an [M, N] buffer of another GPU (CUDA IPC / symmetric memory): typically this rank's slot of every other
