@@ -17,6 +17,7 @@ LIB_PATH = _PKG / ("libconch_b200_dbg.so" if os.environ.get("CB200_DEBUG_LIB") =
 # enums of include/conch_b200.h
 F16, BF16, F32 = 0, 1, 2
 ZP_NONE, ZP_I32, ZP_U8, ZP_ACT = 0, 1, 2, 3
+IN_INT8, IN_FP8_E4M3 = 0, 1
 AUTO, DECODE_MMA, TC_SS, TC_TS, TC2_TS, DECODE_STREAM = 0, 1, 2, 3, 4, 5
 VARIANT_NAMES = {AUTO: "auto", DECODE_MMA: "decode_mma", TC_SS: "tc_ss", TC_TS: "tc_ts", TC2_TS: "tc2_ts", DECODE_STREAM: "decode_stream"}
 ERR_ARG, ERR_SHAPE, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_DEVICE = -1, -2, -3, -4, -5
@@ -29,6 +30,8 @@ EXPORTS = (
     "cb200_mpgemm_workspace_bytes",
     "cb200_mpgemm",
     "cb200_mpgemm_bias",
+    "cb200_scaled_gemm",
+    "cb200_static_scaled_quant",
     "cb200_mpgemm_push",
     "cb200_mpgemm_push_signal",
     "cb200_wait_flags",
@@ -87,6 +90,10 @@ def load() -> ctypes.CDLL:
         ]  # fmt: skip
         lib.cb200_mpgemm_bias.restype = c_int
         lib.cb200_mpgemm_bias.argtypes = lib.cb200_mpgemm.argtypes[:4] + [c_void_p] + lib.cb200_mpgemm.argtypes[4:]  # ..., w_zp, bias, out, ...
+        lib.cb200_scaled_gemm.restype = c_int
+        lib.cb200_scaled_gemm.argtypes = [c_void_p] * 6 + [c_int64] * 3 + [c_int] * 4 + [c_void_p]  # a, b_t, sa, sb, bias, out, M, K, N, ...
+        lib.cb200_static_scaled_quant.restype = c_int
+        lib.cb200_static_scaled_quant.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]
         lib.cb200_mpgemm_push.restype = c_int
         lib.cb200_mpgemm_push.argtypes = lib.cb200_mpgemm.argtypes + [ctypes.POINTER(c_void_p), c_int]  # peer_out, num_peers
         lib.cb200_mpgemm_push_signal.restype = c_int

@@ -333,4 +333,61 @@ int cb200_mpgemm_bias(const void* x, const void* w_q_packed, const void* w_s, co
                     zp_is_scalar, workspace, workspace_bytes, variant, stream, nullptr, 0, nullptr, nullptr, bias);
 }
 
+int cb200_scaled_gemm(const void* a, const void* b_t, const void* scale_a, const void* scale_b, const void* bias, void* out, int64_t M,
+                      int64_t K, int64_t N, int in_kind, int out_dtype, int scale_a_is_scalar, int scale_b_is_scalar, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!a || !b_t || !scale_a || !scale_b || !out) {
+    set_error("null pointer argument");
+    return CB200_ERR_ARG;
+  }
+  if (M <= 0 || K <= 0 || N <= 0 || M > (1 << 24) || K > (1 << 24) || N > (1 << 24)) {
+    set_error("dimension out of range M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
+    return CB200_ERR_ARG;
+  }
+  if (in_kind != CB200_IN_INT8 && in_kind != CB200_IN_FP8_E4M3) {
+    set_error("scaled_gemm input kind %d not supported (int8 or fp8 e4m3)", in_kind);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (out_dtype != CB200_F16 && out_dtype != CB200_BF16 && out_dtype != CB200_F32) {
+    set_error("output dtype %d not supported", out_dtype);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (K % 16 != 0 || N % 8 != 0) {
+    set_error("scaled_gemm needs K %% 16 == 0 and N %% 8 == 0 (K=%lld, N=%lld): rows are fetched by TMA / stored as 16-byte vectors",
+              (long long)K, (long long)N);
+    return CB200_ERR_SHAPE;
+  }
+  if (!aligned16(a) || !aligned16(b_t) || !aligned16(out) || (reinterpret_cast<uintptr_t>(scale_a) & 3u) ||
+      (reinterpret_cast<uintptr_t>(scale_b) & 3u)) {
+    set_error("a, b and out must be 16-byte aligned, the scales 4-byte aligned");
+    return CB200_ERR_ARG;
+  }
+  return launch_scaled(a, b_t, reinterpret_cast<const float*>(scale_a), reinterpret_cast<const float*>(scale_b), bias, out, int(M), int(K),
+                       int(N), in_kind, out_dtype, scale_a_is_scalar, scale_b_is_scalar, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cb200_static_scaled_quant(const void* x, const void* scale, void* out, int64_t n, int in_dtype, int out_kind, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!x || !scale || !out || n < 0) {
+    set_error("null pointer / negative size");
+    return CB200_ERR_ARG;
+  }
+  if (in_dtype != CB200_F16 && in_dtype != CB200_BF16 && in_dtype != CB200_F32) {
+    set_error("input dtype %d not supported (fp16, bf16, fp32)", in_dtype);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (out_kind != CB200_IN_INT8 && out_kind != CB200_IN_FP8_E4M3) {
+    set_error("output kind %d not supported (int8 or fp8 e4m3)", out_kind);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (!aligned16(x) || (reinterpret_cast<uintptr_t>(out) & 7u) || (reinterpret_cast<uintptr_t>(scale) & 3u)) {
+    set_error("x must be 16-byte aligned, out 8-byte aligned, scale 4-byte aligned");
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  return launch_static_quant(x, reinterpret_cast<const float*>(scale), out, n, in_dtype, out_kind, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

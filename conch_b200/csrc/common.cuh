@@ -86,6 +86,9 @@ bool tc_supported(const Problem& p, int bits);
 int launch_stream(const Problem& p, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 size_t stream_workspace_bytes(int64_t M, int64_t K, int64_t N, int bits);
 bool stream_supported(const Problem& p, int bits, int act_dtype);
+int launch_scaled(const void* a, const void* b_t, const float* scale_a, const float* scale_b, const void* bias, void* out, int M,
+                  int K, int N, int in_kind, int out_dtype, int sa_scalar, int sb_scalar, cudaStream_t stream);
+int launch_static_quant(const void* x, const float* scale, void* out, int64_t n, int in_dtype, int out_kind, cudaStream_t stream);
 int launch_wait_flags(const uint32_t* flags, int count, uint32_t* expected, cudaStream_t stream);
 struct StreamTuning {
   int ring_kb;   // shared memory the kernel may use per CTA, in KiB (0 = all of it)

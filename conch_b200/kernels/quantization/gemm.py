@@ -21,17 +21,21 @@ from conch_b200 import _lib
 class WeightGroupMode(Enum):
     """Dequantisation modes (names follow the reference enum, conch/kernels/quantization/gemm.py:34-41).
 
-    Only the two modes reachable from `mixed_precision_gemm` exist here (conch/ops/quantization/gemm.py:34-38).
+    Only the modes reachable from `mixed_precision_gemm` (conch/ops/quantization/gemm.py:34-38) and `scaled_gemm` (:227)
+    exist here.
     """
 
+    NONE = 0  # scaled_gemm: nothing to dequantise
     SYMMETRIC_NO_SHIFT = 2  # W = q * s            (w_zp is None)
     SYMMETRIC_WITH_SHIFT = 3  # W = (q - zp) * s
 
 
 class ChannelScaleMode(Enum):
-    """conch/kernels/quantization/gemm.py:68-74; the mixed-precision frontend always uses NONE."""
+    """conch/kernels/quantization/gemm.py:68-74; the mixed-precision frontend always uses NONE, scaled_gemm always
+    WEIGHT_AND_ACTIVATION."""
 
     NONE = 0
+    WEIGHT_AND_ACTIVATION = 3
 
 
 @dataclass
@@ -56,7 +60,24 @@ class MixedPrecisionMatmulMetadata:
     weight_group_mode: WeightGroupMode
 
 
+@dataclass
+class ScaledMatmulMetadata:
+    """Same 10 fields as the reference dataclass (conch/kernels/quantization/gemm.py:548-561)."""
+
+    m_dim: int
+    k_dim: int
+    n_dim: int
+    data_contiguous: bool
+    input_dtype: torch.dtype
+    output_dtype: torch.dtype
+    acc_dtype: torch.dtype
+    meta_dtype: torch.dtype
+    channel_scale_mode: ChannelScaleMode
+    weight_group_mode: WeightGroupMode
+
+
 _DTYPE_CODE = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+_IN_KIND = {torch.int8: _lib.IN_INT8, torch.float8_e4m3fn: _lib.IN_FP8_E4M3}
 
 # (device index, stream handle) -> uint8 workspace tensor whose counter prefix is zero between launches
 _workspaces: dict[tuple[int, int], torch.Tensor] = {}
@@ -206,3 +227,73 @@ def dequantize_launcher(
             stream,
         )  # fmt: skip
     _lib.raise_for_status(rc)
+
+
+def _k_major(b: torch.Tensor) -> torch.Tensor:
+    """`b` [K, N] as a dense [N, K] tensor (K contiguous): a free view when b is the transpose of a contiguous [N, K] weight --
+    the layout the reference's callers use (tests/scaled_gemm_test.py:68-72) -- else one transposing copy."""
+    bt = b.t()
+    if not bt.is_contiguous() or bt.data_ptr() % 16:
+        bt = bt.contiguous().clone() if bt.is_contiguous() else bt.contiguous()
+    return bt
+
+
+def scaled_gemm_launcher(
+    output: torch.Tensor,
+    a: torch.Tensor,
+    b: torch.Tensor,
+    scale_a: torch.Tensor,
+    scale_b: torch.Tensor,
+    metadata: ScaledMatmulMetadata,
+    *,
+    bias: torch.Tensor | None = None,
+) -> None:
+    """Enqueue out = cast((a @ b) * (scale_a * scale_b^T)) (+ bias) on the current CUDA stream.
+
+    Counterpart of the reference launcher (conch/kernels/quantization/gemm.py:564-627): same argument order; the bias the
+    reference op adds with a second kernel (conch/ops/quantization/gemm.py:249-250) can be handed to the epilogue instead,
+    which reproduces that two-rounding arithmetic."""
+    lib = _lib.load()
+    if metadata.input_dtype not in _IN_KIND:
+        raise NotImplementedError(f"scaled_gemm input dtype {metadata.input_dtype} (int8 or float8_e4m3fn)")
+    device = a.device
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    a = a.contiguous()
+    if a.data_ptr() % 16:
+        a = a.clone()
+    bt = _k_major(b)
+    sa = scale_a.to(torch.float32).contiguous().reshape(-1)
+    sb = scale_b.to(torch.float32).contiguous().reshape(-1)
+    with torch.cuda.device(device):
+        rc = lib.cb200_scaled_gemm(
+            a.data_ptr(), bt.data_ptr(), sa.data_ptr(), sb.data_ptr(), None if bias is None else bias.data_ptr(), output.data_ptr(),
+            metadata.m_dim, metadata.k_dim, metadata.n_dim, _IN_KIND[metadata.input_dtype], _DTYPE_CODE[metadata.output_dtype],
+            int(sa.numel() == 1), int(sb.numel() == 1), _raw_stream(index),
+        )  # fmt: skip
+    _lib.raise_for_status(rc)
+
+
+def static_scaled_quant_launcher(output_tensor: torch.Tensor, input_tensor: torch.Tensor, scale: torch.Tensor) -> None:
+    """Enqueue output = quantise(input / scale) for a whole tensor: int8 or float8_e4m3fn, by the dtype of `output_tensor`.
+    Counterpart of static_scaled_int8_quant_launcher / static_scaled_fp8_quant_launcher
+    (conch/kernels/quantization/int8.py:61-97, fp8.py:67-97)."""
+    lib = _lib.load()
+    if output_tensor.dtype not in _IN_KIND:
+        raise NotImplementedError(f"quantised dtype {output_tensor.dtype} (int8 or float8_e4m3fn)")
+    if input_tensor.dtype not in _DTYPE_CODE:
+        raise NotImplementedError(f"input dtype {input_tensor.dtype} (fp16, bf16 or fp32)")
+    if not output_tensor.is_contiguous():
+        raise ValueError("output_tensor must be contiguous")
+    device = input_tensor.device
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    x = input_tensor.contiguous()
+    if x.data_ptr() % 16:
+        x = x.clone()
+    s = scale.to(torch.float32).contiguous()
+    with torch.cuda.device(device):
+        rc = lib.cb200_static_scaled_quant(
+            x.data_ptr(), s.data_ptr(), output_tensor.data_ptr(), x.numel(), _DTYPE_CODE[x.dtype], _IN_KIND[output_tensor.dtype],
+            _raw_stream(index),
+        )  # fmt: skip
+    _lib.raise_for_status(rc)
+

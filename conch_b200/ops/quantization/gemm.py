@@ -20,10 +20,12 @@ import torch
 from conch_b200 import _lib
 from conch_b200.kernels.quantization.gemm import (
     ChannelScaleMode,
-    MixedPrecisionMatmulMetadata,
-    WeightGroupMode,
     dequantize_launcher,
     mixed_precision_gemm_launcher,
+    MixedPrecisionMatmulMetadata,
+    scaled_gemm_launcher,
+    ScaledMatmulMetadata,
+    WeightGroupMode,
 )
 from conch_b200.platform import current_platform
 
@@ -303,3 +305,79 @@ def dequantize_weights(
         weight_size_bits, weight_bias, group_size,
     )  # fmt: skip
     return out
+
+
+def create_scaled_metadata(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    scale_a: torch.Tensor,
+    scale_b: torch.Tensor,
+    output_dtype: torch.dtype,
+    strict: bool = False,
+) -> ScaledMatmulMetadata:
+    """Verify sizes and dtypes of tensors and deduce metadata parameters (reference conch/ops/quantization/gemm.py:171-230:
+    same checks, same messages, same result)."""
+    if strict:
+        expected_input_matrix_rank = 2
+        if (a_rank := len(a.shape)) != expected_input_matrix_rank:
+            raise ValueError(f"Unexpected number of dimensions of input tensor a: {a_rank}")
+        if (b_rank := len(b.shape)) != expected_input_matrix_rank:
+            raise ValueError(f"Unexpected number of dimensions of input tensor b: {b_rank}")
+        if a.dtype != b.dtype:
+            raise ValueError(f"Input tensors a and b must have the same datatype (a: {a.dtype}, b: {b.dtype})")
+    m_dim, k_dim = a.shape
+    _, n_dim = b.shape
+    if strict:
+        if scale_a.numel() != 1:
+            if (scale_a_rank := len(scale_a.shape)) != expected_input_matrix_rank:
+                raise ValueError(f"Unexpected number of dimensions of input tensor scale_a: {scale_a_rank}")
+            if scale_a.shape[0] != m_dim:
+                raise ValueError(f"Invalid scale_a shape (expected: ({m_dim},), actual: {scale_a.shape})")
+        if scale_b.numel() != 1:
+            if (scale_b_rank := len(scale_b.shape)) != expected_input_matrix_rank:
+                raise ValueError(f"Unexpected number of dimensions of input tensor scale_b: {scale_b_rank}")
+            if scale_b.shape[0] != n_dim:
+                raise ValueError(f"Invalid scale_b shape (expected: ({n_dim},), actual: {scale_b.shape})")
+    return ScaledMatmulMetadata(
+        m_dim=m_dim,
+        k_dim=k_dim,
+        n_dim=n_dim,
+        data_contiguous=(a.is_contiguous() and b.is_contiguous() and scale_a.is_contiguous() and scale_b.is_contiguous()),
+        input_dtype=a.dtype,
+        output_dtype=output_dtype,
+        acc_dtype=torch.float32 if a.is_floating_point() else torch.int32,
+        meta_dtype=scale_a.dtype,
+        channel_scale_mode=ChannelScaleMode.WEIGHT_AND_ACTIVATION,
+        weight_group_mode=WeightGroupMode.NONE,
+    )
+
+
+def scaled_gemm(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    scale_a: torch.Tensor,
+    scale_b: torch.Tensor,
+    output_dtype: torch.dtype,
+    bias: torch.Tensor | None = None,
+    strict: bool = False,
+) -> torch.Tensor:
+    """Scaled GEMM: `cast((a[M,K] @ b[K,N]) * (scale_a[M,1] * scale_b[N,1]^T)) (+ bias[N])` for int8 / float8_e4m3fn operands.
+
+    Signature of the reference op (conch/ops/quantization/gemm.py:233-252).  The bias goes into the kernel's epilogue, which
+    reproduces the reference's two-kernel arithmetic (round, add, round)."""
+    _require_device(a, b, scale_a, scale_b, bias)
+    metadata = create_scaled_metadata(a, b, scale_a, scale_b, output_dtype, strict=strict)
+    if a.dtype != b.dtype:
+        raise ValueError(f"Input tensors a and b must have the same datatype (a: {a.dtype}, b: {b.dtype})")
+    if scale_a.numel() not in (1, metadata.m_dim) or scale_b.numel() not in (1, metadata.n_dim):
+        raise ValueError(f"scale_a / scale_b must have 1 or M / N elements (got {scale_a.numel()}, {scale_b.numel()})")
+    if bias is not None:
+        if bias.numel() != metadata.n_dim:
+            raise ValueError(f"`bias` must have N = {metadata.n_dim} elements")
+        bias = bias.to(output_dtype).contiguous().reshape(-1)
+    output = torch.empty((metadata.m_dim, metadata.n_dim), device=a.device, dtype=output_dtype)
+    if metadata.m_dim == 0 or metadata.n_dim == 0:
+        return output
+    scaled_gemm_launcher(output, a, b, scale_a, scale_b, metadata, bias=bias)
+    return output
+

@@ -49,6 +49,9 @@ extern "C" {
 /* element types (activations, scales, outputs) */
 enum cb200_dtype { CB200_F16 = 0, CB200_BF16 = 1, CB200_F32 = 2 };
 
+/* 8-bit operand formats of the scaled-GEMM sibling path (reference: torch.int8 / torch.float8_e4m3fn) */
+enum cb200_in_kind { CB200_IN_INT8 = 0, CB200_IN_FP8_E4M3 = 1 };
+
 /* what `w_zp` points at (reference: w_zp None / int32 from quantize_weights / uint8 from vLLM / meta dtype) */
 enum cb200_zp_kind { CB200_ZP_NONE = 0, CB200_ZP_I32 = 1, CB200_ZP_U8 = 2, CB200_ZP_ACT = 3 };
 
@@ -153,6 +156,28 @@ CB200_API int cb200_dequantize(const void* w_q_packed, const void* w_s, const vo
                      int64_t K, int64_t N,
                      int weight_size_bits, int weight_bias, int64_t group_size,
                      int act_dtype, int zp_kind, int zp_is_scalar, void* stream);
+
+/* out[M,N] = cast( (a[M,K] @ b[K,N]) * (scale_a[m] * scale_b[n]) ) (+ bias[n]): W8A8 GEMM with per-token x per-channel scales.
+ *   a        [M, K] int8 | fp8 e4m3, row-major
+ *   b_t      [N, K] same type, row-major -- the reference's `b` ([K, N]) in the layout its callers hand it, b = w.T with w
+ *            contiguous (tests/scaled_gemm_test.py:68-72); the host side transposes anything else once
+ *   scale_a  fp32 [M] or 1 element (scale_a_is_scalar); scale_b fp32 [N] or 1 element
+ *   bias     [N] in the output dtype or NULL; added to the ROUNDED product and rounded again, as the reference's
+ *            `output.add_(bias)` does (conch/ops/quantization/gemm.py:249-250)
+ *   out      [M, N] fp16 | bf16 | fp32
+ * K % 16 == 0, N % 8 == 0, every pointer 16-byte aligned.  int8 results are bit-identical to the reference op's arithmetic
+ * (exact int32 accumulation, acc * (scale_a * scale_b) in fp32, one rounding).
+ * Replaces: scaled_gemm_launcher(output, a, b, scale_a, scale_b, metadata) (reference conch/kernels/quantization/gemm.py:564-627). */
+CB200_API int cb200_scaled_gemm(const void* a, const void* b_t, const void* scale_a, const void* scale_b, const void* bias, void* out,
+                 int64_t M, int64_t K, int64_t N, int in_kind, int out_dtype,
+                 int scale_a_is_scalar, int scale_b_is_scalar, void* stream);
+
+/* out[i] = quantise(x[i] * (1 / scale[0])) for a whole tensor of n elements: int8 (clamp to [-128, 127], truncation toward
+ * zero) or fp8 e4m3 (clamp to +-448, round to nearest even).  x fp16 | bf16 | fp32 (in_dtype), scale fp32 [1], out 1 byte per
+ * element.  x must be 16-byte aligned, out 8-byte aligned.
+ * Replaces: static_scaled_int8_quant_launcher / static_scaled_fp8_quant_launcher
+ *           (reference conch/kernels/quantization/int8.py:61-97, fp8.py:67-97). */
+CB200_API int cb200_static_scaled_quant(const void* x, const void* scale, void* out, int64_t n, int in_dtype, int out_kind, void* stream);
 
 /* Debug/tuning knobs of the decode kernel (0 = heuristic).  Process-global, not thread-safe.
  *   warps_n   1: dequantise every weight before the MMA (W bits equal the reference's w_ref); 2: fused magic-number operands;
