@@ -17,6 +17,21 @@ class _Platform:
     def has_cuda(self) -> bool:
         return True
 
+    def is_amd(self) -> bool:
+        return False
+
+    def is_xpu(self) -> bool:
+        return False
+
+    def is_unspecified(self) -> bool:
+        return False
+
+    def supports_fp8(self) -> bool:
+        return True  # sm_100: e4m3 / e5m2 tensor-core operands (reference conch/platforms/platform.py:50-60)
+
+    def name(self) -> str:
+        return "nvidia"
+
     @functools.lru_cache(maxsize=None)  # noqa: B019
     def check(self, index: int | None = None) -> None:
         if not torch.cuda.is_available():

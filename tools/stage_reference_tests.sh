@@ -7,5 +7,7 @@ set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 REF="${1:-/root/reference}"
 mkdir -p "$ROOT/baseline/_ref_tests"
-cp "$REF/tests/mixed_precision_gemm_test.py" "$ROOT/baseline/_ref_tests/"
+for t in mixed_precision_gemm_test.py scaled_gemm_test.py int8_quant_kernels_test.py fp8_quant_kernels_test.py; do
+  cp "$REF/tests/$t" "$ROOT/baseline/_ref_tests/"
+done
 echo "staged $(ls "$ROOT/baseline/_ref_tests")"
