@@ -32,12 +32,15 @@ def main() -> None:
     ap.add_argument("--wtype", default="uint4")
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--group", type=int, default=128)
+    ap.add_argument("--no-hint", action="store_true", help="stream kernel without the L2 evict_first policy on the weight tiles (A/B)")
     args = ap.parse_args()
     lib = _lib.load()
     pk = peaks()
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
     st = getattr(quant_utils.scalar_types, args.wtype)
     lib.cb200_set_pdl(1)
+    if args.no_hint:
+        lib.cb200_set_stream_tuning(-224, 0)
     with open(args.out, "w") as f:
         for name, m in itertools.product(args.shapes.split(","), [int(v) for v in args.ms.split(",")]):
             k, n = SHAPES[name]
@@ -65,6 +68,7 @@ def main() -> None:
                 cells.append(f"{fam} {us:7.2f} us {100 * roof_us / us:5.1f}%")
             print(f"{name:8s} M={m:3d} ({algo / 1e6:5.1f} MB, roof {roof_us:6.2f} us):  " + "   ".join(cells), flush=True)
     lib.cb200_set_pdl(0)
+    lib.cb200_set_stream_tuning(0, 0)
 
 
 if __name__ == "__main__":

@@ -138,7 +138,10 @@ void cb200_set_decode_tuning(int warps_n, int warps_k, int split_k, int vec_word
 void cb200_set_tc_tuning(int m_tile, int split_k) { g_tc_tuning = {m_tile, split_k}; }
 void cb200_set_tc_cluster(int ctas) { g_tc_cluster = (ctas == 1 || ctas == 2 || ctas == 4) ? ctas : 0; }
 void cb200_set_pdl(int enable) { g_decode_pdl = enable ? 1 : 0; }
-void cb200_set_stream_tuning(int ring_kb, int ctas) { g_stream_tuning = {ring_kb, ctas, g_stream_tuning.dbg}; }
+void cb200_set_stream_tuning(int ring_kb, int ctas) {
+  // (ring_kb < 0: debug -- |ring_kb| with the weight tiles loaded WITHOUT the L2 evict_first policy, for A/B timing)
+  g_stream_tuning = {ring_kb < 0 ? -ring_kb : ring_kb, ctas, ring_kb < 0 ? 1 : 0};
+}
 void cb200_debug_set_stream_trace(void* device_buffer) { g_stream_trace = reinterpret_cast<long long*>(device_buffer); }
 
 size_t cb200_mpgemm_workspace_bytes(int64_t M, int64_t K, int64_t N, int weight_size_bits, int variant) {

@@ -93,7 +93,7 @@ int launch_wait_flags(const uint32_t* flags, int count, uint32_t* expected, cuda
 struct StreamTuning {
   int ring_kb;   // shared memory the kernel may use per CTA, in KiB (0 = all of it)
   int ctas;      // upper bound on the CTAs launched (0 = one per SM)
-  int dbg;       // unused
+  int dbg;       // bit 0: no L2 cache policy on the weight tiles (A/B timing)
 };
 extern StreamTuning g_stream_tuning;
 extern long long* g_stream_trace;  // device buffer the next stream_kernel launches stamp (nullptr = off)

@@ -7,11 +7,12 @@
 //
 // Design: a plain warp-specialised tcgen05 GEMM -- there is nothing to dequantise, both operands go from HBM to the tensor
 // core untouched.
-//   * 128 x 128 output tile per CTA, K in 128-byte blocks; warp 0 = TMA producer (a tile [128 m x 128 B] and b^T tile
-//     [128 n x 128 B], both K-major, 128-byte swizzled, a 3-stage ring), warp 1 = MMA issuer (tcgen05.mma kind::i8 /
-//     kind::f8f6f4, M = 128, N = 128, K = 32 per instruction, accumulator in TMEM), warps 2-5 = epilogue (tcgen05.ld, scales,
-//     rounding, 16-byte stores).
-//   * two CTAs per SM (96 KB of ring + 128 TMEM columns each): one CTA's epilogue overlaps the other's main loop.
+//   * 128 x BN output tile per CTA (BN = 256, or 128 for small problems), K in 128-byte blocks; warp 0 = TMA producer (a tile
+//     [128 m x 128 B] and b^T tile [BN n x 128 B], both K-major, 128-byte swizzled, a 3/4-stage ring), warp 1 = MMA issuer
+//     (tcgen05.mma kind::i8 / kind::f8f6f4, M = 128, N = BN, K = 32 per instruction, accumulator in TMEM), warps 2-5 = epilogue
+//     (tcgen05.ld, scales, rounding, 16-byte stores).
+//   * BN = 128: two CTAs per SM (96 KB of ring + 128 TMEM columns each), one CTA's epilogue overlaps the other's main loop;
+//     BN = 256: one CTA per SM with a 192 KB ring -- 175 instead of 128 flop per operand byte, which an 8-bit tile needs.
 //   * arithmetic of the epilogue is the reference kernel's, operation for operation: acc -> fp32, times (scale_a * scale_b)
 //     (the scale PRODUCT first, :431-440), one rounding to the output dtype; a bias is then added to the ROUNDED value and
 //     rounded again, exactly what `output.add_(bias)` computes -- so int8 results are bit-identical to the reference op's.
@@ -32,9 +33,12 @@ struct ScaledParams {
 };
 
 namespace scaled {
-constexpr int BM = 128, BN = 128, BK = 128, STAGES = 3;
-constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int BM = 128, BK = 128;
+template <int BN, int STAGES>
+struct Tile {
+  static constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+};
 
 template <int KIND>
 __device__ __forceinline__ void umma_ss8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -61,11 +65,12 @@ __device__ __forceinline__ float round_out(float v, int out_dtype) {
 }
 }  // namespace scaled
 
-// KIND 0: int8 (s8 x s8 -> s32), 1: fp8 e4m3 (-> f32)
-template <int KIND>
-__global__ void __launch_bounds__(192, 2)
+// KIND 0: int8 (s8 x s8 -> s32), 1: fp8 e4m3 (-> f32); BN: tile width (UMMA N), STAGES: ring depth
+template <int KIND, int BN, int STAGES>
+__global__ void __launch_bounds__(192, BN == 128 ? 2 : 1)
     scaled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ScaledParams prm) {
   using namespace scaled;
+  constexpr int A_BYTES = Tile<BN, STAGES>::A_BYTES, STAGE_BYTES = Tile<BN, STAGES>::STAGE_BYTES;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(192, 2)
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);  // 128 fp32 / int32 columns x 128 lanes: the accumulator
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);  // BN fp32 / int32 columns x 128 lanes: the accumulator
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -182,14 +187,17 @@ __global__ void __launch_bounds__(192, 2)
   if (warp == 1) tmem_dealloc<BN>(tmem_base);
 }
 
-template <int KIND>
+template <int KIND, int BN, int STAGES>
 static int launch_scaled_kind(const CUtensorMap& ma, const CUtensorMap& mb, const ScaledParams& prm, int tiles, cudaStream_t stream) {
   static unsigned long long attr_mask = 0;
-  if (int rc = set_max_smem_once(scaled_kernel<KIND>, scaled::SMEM_BYTES, attr_mask)) return rc;
-  scaled_kernel<KIND><<<tiles, 192, scaled::SMEM_BYTES, stream>>>(ma, mb, prm);
+  constexpr int SMEM = scaled::Tile<BN, STAGES>::SMEM_BYTES;
+  if (int rc = set_max_smem_once(scaled_kernel<KIND, BN, STAGES>, SMEM, attr_mask)) return rc;
+  scaled_kernel<KIND, BN, STAGES><<<tiles, 192, SMEM, stream>>>(ma, mb, prm);
   CB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+int g_scaled_tile = 0;  // debug: 128 / 256 forces the tile width (0 = heuristic)
 
 int launch_scaled(const void* a, const void* b_t, const float* scale_a, const float* scale_b, const void* bias, void* out, int M,
                   int K, int N, int in_kind, int out_dtype, int sa_scalar, int sb_scalar, cudaStream_t stream) {
@@ -198,8 +206,19 @@ int launch_scaled(const void* a, const void* b_t, const float* scale_a, const fl
     set_error("cuTensorMapEncodeTiled driver entry point not available");
     return CB200_ERR_DEVICE;
   }
+  // tile width: 256 columns halve the re-reads of `a` (175 instead of 128 flop per byte of operand traffic -- at 8 bits a
+  // 128 x 128 tile wants more bytes per clock than an SM can pull from L2)
+  const int sms = current_device_info() ? current_device_info()->sms : 148;
+  const int m_tiles = (M + scaled::BM - 1) / scaled::BM;
+  // (measured, profiles/r02_scaled_gemm_bench.log: with one CTA per SM the 256-wide tile's un-overlapped epilogue costs more
+  //  than its operand traffic saves -- 1097 vs 1449 TFLOP/s at 4096 x 4096 x 14336 -- so 128 stays the default until the
+  //  kernel is persistent with a second TMEM accumulator)
+  (void)sms;
+  int bn = 128;
+  if (g_scaled_tile == 128 || g_scaled_tile == 256) bn = g_scaled_tile;
   CUtensorMap ma, mb;
   const cuuint32_t box[2] = {scaled::BK, scaled::BM};
+  const cuuint32_t box_b[2] = {scaled::BK, cuuint32_t(bn)};
   const cuuint32_t estr[2] = {1, 1};
   const cuuint64_t strides[1] = {cuuint64_t(K)};
   {
@@ -213,7 +232,7 @@ int launch_scaled(const void* a, const void* b_t, const float* scale_a, const fl
   }
   {
     const cuuint64_t dims[2] = {cuuint64_t(K), cuuint64_t(N)};
-    const CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(b_t), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(b_t), dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(b) failed: %d", int(r));
@@ -231,10 +250,15 @@ int launch_scaled(const void* a, const void* b_t, const float* scale_a, const fl
   prm.sa_scalar = sa_scalar;
   prm.sb_scalar = sb_scalar;
   prm.out_dtype = out_dtype;
-  prm.n_tiles = (N + scaled::BN - 1) / scaled::BN;
+  prm.n_tiles = (N + bn - 1) / bn;
   prm.kblocks = (K + scaled::BK - 1) / scaled::BK;
-  const int tiles = prm.n_tiles * ((M + scaled::BM - 1) / scaled::BM);
-  return in_kind == CB200_IN_INT8 ? launch_scaled_kind<0>(ma, mb, prm, tiles, stream) : launch_scaled_kind<1>(ma, mb, prm, tiles, stream);
+  const int tiles = prm.n_tiles * m_tiles;
+  if (bn == 256) {
+    return in_kind == CB200_IN_INT8 ? launch_scaled_kind<0, 256, 4>(ma, mb, prm, tiles, stream)
+                                    : launch_scaled_kind<1, 256, 4>(ma, mb, prm, tiles, stream);
+  }
+  return in_kind == CB200_IN_INT8 ? launch_scaled_kind<0, 128, 3>(ma, mb, prm, tiles, stream)
+                                  : launch_scaled_kind<1, 128, 3>(ma, mb, prm, tiles, stream);
 }
 
 }  // namespace cb200

@@ -33,6 +33,7 @@ struct StreamGeom {
   int x_bytes;      // staged x slab
   int red_bytes;    // cluster reduction buffers + the group sums of x (at its end)
   int xsum_bytes;
+  int no_hint;      // debug (cb200_set_stream_tuning ring_kb < 0): weight tiles without the L2 evict_first policy
   unsigned int* done;  // cb200_mpgemm_push_signal: self-resetting counter of finished 32-column slices (workspace), else unused
   long long* trace; // debug builds: [CTA][8] globaltimer stamps
 };
@@ -64,6 +65,19 @@ __device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, int
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
                "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                : "memory");
+}
+// same, with an L2 cache policy (the weights are read exactly once: evict_first keeps them from displacing the activations,
+// scales and zero-points that ARE re-read, by this kernel's other CTAs and by the next kernels)
+__device__ __forceinline__ void tma_3d_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ float4 lds128f(uint32_t a) {
   float4 v;
@@ -266,6 +280,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
     const char* sp = reinterpret_cast<const char*>(p.s) + size_t(cb) * BN * 2;
     const char* zp = reinterpret_cast<const char*>(p.zp) + size_t(cb) * BN * geo.zes;
     const size_t s_pitch = size_t(N) * 2, z_pitch = size_t(N) * geo.zes;
+    const uint64_t stream_policy = policy_evict_first();
     int grp0 = geo.one_group ? 0 : qa0 / qpg;  // first scale group of the stage; rem: quads of that group in front of the stage
     int rem = geo.one_group ? 0 : qa0 - grp0 * qpg;
     for (int i = 0; i < nstages; ++i) {
@@ -275,7 +290,8 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
       const int ng = min(geo.gps, geo.ngroups - grp0);
       if (leader) {
         mbar_expect_tx(fb, uint32_t(geo.w_bytes) + uint32_t(ng) * (srow_bytes + zrow_bytes));
-        tma_3d(dst, &tmw, 0, (qa0 + 4 * i) * 4, cb * nw, fb);
+        if (geo.no_hint) tma_3d(dst, &tmw, 0, (qa0 + 4 * i) * 4, cb * nw, fb);
+        else tma_3d_hint(dst, &tmw, 0, (qa0 + 4 * i) * 4, cb * nw, fb, stream_policy);
 #pragma unroll 1
         for (int j = 0; j < ng; ++j) {
           bulk_g2s(dst + s_off + j * BN * 2, sp + size_t(grp0 + j) * s_pitch, srow_bytes, fb);

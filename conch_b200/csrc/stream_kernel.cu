@@ -205,6 +205,7 @@ int launch_stream(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     geo.red_bytes = pl.red_bytes;
     geo.xsum_bytes = pl.xsum_bytes;
     geo.done = ws ? reinterpret_cast<unsigned int*>(ws) + (CB200_WORKSPACE_COUNTER_BYTES / 4 - 1) : nullptr;
+    geo.no_hint = g_stream_tuning.dbg & 1;
     geo.trace = g_stream_trace;
     const bool pdl = g_decode_pdl != 0;
     int rc;
