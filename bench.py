@@ -248,6 +248,7 @@ def run_gpu_arm(args) -> None:
     # Programmatic dependent launch: each GEMV prefetches its (static) weights while the previous one drains.
     # Legal here because no kernel in the step writes weights (include/conch_b200.h, cb200_set_pdl).
     lib.cb200_set_pdl(0 if args.no_pdl else 1)
+    push_variant = int(os.environ.get("CB200_BENCH_PUSH_VARIANT", "0"))  # debug: kernel family of the fused-gather GEMVs (0 = AUTO)
 
     # ---- synthetic model: 32 layers x 4 projections, drawn directly in the packed domain ------------------------
     st = quant_utils.scalar_types.uint4
@@ -286,7 +287,7 @@ def run_gpu_arm(args) -> None:
                     pending = work
                 elif world > 1:
                     # fused gather: the GEMV kernel's epilogue stores its slice into every rank's gather buffer (P2P)
-                    sharded[layer][pi].pushed(xs[pi])
+                    sharded[layer][pi].pushed(xs[pi], variant=push_variant)
                 else:
                     mixed_precision_gemm(xs[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=outs[layer][pi])
                 if count:
@@ -368,7 +369,7 @@ def run_gpu_arm(args) -> None:
                         pending.wait()
                     pending = work
                 elif world > 1:
-                    sharded[layer][pi].pushed(x_dev[pi])
+                    sharded[layer][pi].pushed(x_dev[pi], variant=push_variant)
                 else:
                     mixed_precision_gemm(x_dev[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=out_views[layer][pi].view(M, -1))
         if pending is not None:

@@ -275,8 +275,10 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
     // register-window kernel (bf16 x int8, group sizes that straddle stages); tcgen05 pipeline above.
     const bool decode = M <= 8;
     if (decode || !tc_supported(p, weight_size_bits)) {
-      chosen = (decode && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM
-                                                                                                       : CB200_DECODE_MMA;
+      // (fused gather to 4 or more peers: the register-window kernel, whose column blocks finish -- and push -- at staggered
+      //  times; the streaming kernel's CTAs all store in the same microsecond and the kernel then sits out a full NVLink
+      //  round trip: measured 1.71-3.1 ms against 1.57 ms per 8-GPU step, profiles/r02_bench_n8*.json)
+      chosen = (decode && num_peers < 4 && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM : CB200_DECODE_MMA;
     } else {
       chosen = CB200_TC_TS;
     }

@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
 
   DEC_STAMP(6);
   constexpr bool HALF = std::is_same<A, __half>::value;
-  constexpr bool PRESCALE = FUSED && HALF && BITS == 4;  // nibbles at bits 4-7 arrive as 16 q: their activations get x 1/16
+  // fp16 x int4: nibbles at bits 4-7 arrive as 16 q.  They accumulate in their OWN accumulator (accq), which is scaled by 1/16
+  // in fp32 when the group closes (round 1 pre-multiplied their activations by 1/16 in fp16 instead, which lost bits for
+  // |x| < 2^-10 -- ADVICE r1)
+  constexpr bool SPLITQ = FUSED && HALF && BITS == 4;
   // XS: the group sums X[g][m] = sum_k x[m,k] are computed ONCE per CTA from the staged slab (deterministic two-pass
   // reduction below) instead of by an all-ones MMA per operand pair in every warp, and (int4) the slab is rewritten in the
   // operand order the main loop wants -- pairs (k0,k4),(k1,k5),(k2,k6),(k3,k7), the x16 partners pre-scaled by 1/16 -- so a
@@ -208,10 +211,6 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
           uint32_t o1 = __byte_perm(v.x, v.z, 0x7632);  // (k1,k5)
           uint32_t o2 = __byte_perm(v.y, v.w, 0x5410);  // (k2,k6)
           uint32_t o3 = __byte_perm(v.y, v.w, 0x7632);  // (k3,k7)
-          if constexpr (PRESCALE) {
-            o1 = ActOps<A>::mul(o1, 0x2C002C00u);
-            o3 = ActOps<A>::mul(o3, 0x2C002C00u);
-          }
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
         }
       }
@@ -247,7 +246,6 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   constexpr float MAGIC = HALF ? 0.f : 128.f;           // bf16 operands are 128 + q; fp16 operands are q * 2^-24
   constexpr float OPSCALE = HALF ? 16777216.f : 1.f;    // 2^24 undoes the subnormal scaling
   constexpr uint32_t ONE2 = HALF ? 0x3C003C00u : 0x3F803F80u;      // (1.0, 1.0)
-  constexpr uint32_t ONE2_ODD = PRESCALE ? 0x4C004C00u : ONE2;     // (16.0, 16.0) against activations scaled by 1/16
 
   ColQ cq[VEC];          // !FUSED: per-column dequant constants
   float sa[VEC];         // FUSED: s[n] * 2^24 (fp16) | s[n] (bf16): multiplies G = sum_k x * operand
@@ -256,13 +254,17 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
   float acc[NT][MT][4];   // running (scaled) sum of this warp's slab
   float accg[NT][MT][4];  // FUSED: G of the current group (exact products, fp32 sum)
+  float accq[SPLITQ ? NT : 1][MT][4];  // SPLITQ: the x16 operands' share of G
   float accx[MT][4];      // FUSED: X[m] = sum_k x[m,k] of the current group, in the accumulator layout
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[t][mt][i] = accg[t][mt][i] = accx[mt][i] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        acc[t][mt][i] = accg[t][mt][i] = accx[mt][i] = 0.f;
+        if constexpr (SPLITQ) accq[t][mt][i] = 0.f;
+      }
   bool group_open = false;  // FUSED: accg holds a partial group
 
   auto close_group = [&]() {  // FUSED: acc += sa[n] * G[m,n] + sb[n] * X[m]
@@ -282,7 +284,9 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float off = fmaf(sb[2 * t + (i >> 1)], accx[mt][i], acc[t][mt][i]);
-          acc[t][mt][i] = fmaf(sa[2 * t + (i >> 1)], accg[t][mt][i], off);
+          float G = accg[t][mt][i];
+          if constexpr (SPLITQ) G = fmaf(accq[t][mt][i], 0.0625f, G);
+          acc[t][mt][i] = fmaf(sa[2 * t + (i >> 1)], G, off);
         }
   };
 
@@ -375,29 +379,44 @@ __global__ void __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          if constexpr (PRESCALE && !XS) {  // activations that meet the x16 operands: x * 1/16
-            xb[mt][1] = ActOps<A>::mul(xb[mt][1], 0x2C002C00u);
-            xb[mt][3] = ActOps<A>::mul(xb[mt][3], 0x2C002C00u);
-          }
-#pragma unroll
-          for (int h = 0; h < PAIRS / 2; ++h) {
+          if constexpr (SPLITQ) {
+            // plain operands (k0,k4),(k2,k6) -> accg; x16 operands (k1,k5),(k3,k7) -> accq; X from both activation pairs
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-              // data: rows g8 <- column 2t, rows g8+8 <- column 2t+1; operand pair 2h is plain, 2h+1 is the x16 kind
-              if (fresh && h == 0) {
-                mma16816<A>(accg[t][mt], zero4, d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1], d[2 * t + 1][2 * h + 1],
-                            xb[mt][2 * h], xb[mt][2 * h + 1]);
+              if (fresh) {
+                mma16816<A>(accg[t][mt], zero4, d[2 * t][0], d[2 * t + 1][0], d[2 * t][2], d[2 * t + 1][2], xb[mt][0], xb[mt][2]);
+                mma16816<A>(accq[t][mt], zero4, d[2 * t][1], d[2 * t + 1][1], d[2 * t][3], d[2 * t + 1][3], xb[mt][1], xb[mt][3]);
               } else {
-                mma16816<A>(accg[t][mt], accg[t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
-                            d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
+                mma16816<A>(accg[t][mt], accg[t][mt], d[2 * t][0], d[2 * t + 1][0], d[2 * t][2], d[2 * t + 1][2], xb[mt][0], xb[mt][2]);
+                mma16816<A>(accq[t][mt], accq[t][mt], d[2 * t][1], d[2 * t + 1][1], d[2 * t][3], d[2 * t + 1][3], xb[mt][1], xb[mt][3]);
               }
             }
-            // X[m] += sum_k x[m,k] over this operand pair's 16 k (all 16 rows of the result are equal)
             if constexpr (!XS) {
-              if (fresh && h == 0) {
-                mma16816<A>(accx[mt], zero4, ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
-              } else {
-                mma16816<A>(accx[mt], accx[mt], ONE2, ONE2, ONE2_ODD, ONE2_ODD, xb[mt][2 * h], xb[mt][2 * h + 1]);
+              if (fresh) mma16816<A>(accx[mt], zero4, ONE2, ONE2, ONE2, ONE2, xb[mt][0], xb[mt][2]);
+              else mma16816<A>(accx[mt], accx[mt], ONE2, ONE2, ONE2, ONE2, xb[mt][0], xb[mt][2]);
+              mma16816<A>(accx[mt], accx[mt], ONE2, ONE2, ONE2, ONE2, xb[mt][1], xb[mt][3]);
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < PAIRS / 2; ++h) {
+#pragma unroll
+              for (int t = 0; t < NT; ++t) {
+                // data: rows g8 <- column 2t, rows g8+8 <- column 2t+1
+                if (fresh && h == 0) {
+                  mma16816<A>(accg[t][mt], zero4, d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1], d[2 * t + 1][2 * h + 1],
+                              xb[mt][2 * h], xb[mt][2 * h + 1]);
+                } else {
+                  mma16816<A>(accg[t][mt], accg[t][mt], d[2 * t][2 * h], d[2 * t + 1][2 * h], d[2 * t][2 * h + 1],
+                              d[2 * t + 1][2 * h + 1], xb[mt][2 * h], xb[mt][2 * h + 1]);
+                }
+              }
+              // X[m] += sum_k x[m,k] over this operand pair's 16 k (all 16 rows of the result are equal)
+              if constexpr (!XS) {
+                if (fresh && h == 0) {
+                  mma16816<A>(accx[mt], zero4, ONE2, ONE2, ONE2, ONE2, xb[mt][2 * h], xb[mt][2 * h + 1]);
+                } else {
+                  mma16816<A>(accx[mt], accx[mt], ONE2, ONE2, ONE2, ONE2, xb[mt][2 * h], xb[mt][2 * h + 1]);
+                }
               }
             }
           }

@@ -77,9 +77,9 @@ struct DecodePlan {
 };
 
 // Every knob is overridable through cb200_set_decode_tuning(warps_n -> 1: per-weight dequant before the MMA (W bits
-// identical to the reference's w_ref), 2: fused magic-number operands (measured 5-10% faster), 0: fused except for
-// fp16 x int4 (`exact_default`), whose fused form pre-multiplies half of the activations by 1/16 IN FP16 and so loses bits
-// for |x| < 2^-10 -- ADVICE r1; that format's fast path is the streaming kernel, which scales an accumulator instead;
+// identical to the reference's w_ref), 0 / 2 (default, measured 5-10% faster): fused magic-number operands -- for fp16 x int4
+// the x16 nibbles accumulate separately and that accumulator is scaled by 1/16 in fp32 (round 1 scaled their activations in
+// fp16 and lost bits for |x| < 2^-10);
 // warps_k -> CTAs per SM assumed resident; split_k -> forced split count S (rounded down to a legal divisor); vec_words unused).
 static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g, bool exact_default = false) {
   DecodePlan pl;
@@ -88,7 +88,8 @@ static DecodePlan decode_plan(int mrows, int K, int N, int bits, int g, bool exa
   const int B = K / (pl.u * step_k);  // batches per column block
   pl.bpg = g / (pl.u * step_k);
   pl.col_blocks = N / 32;
-  pl.fused = g_decode_tuning.warps_n == 2 || (g_decode_tuning.warps_n == 0 && !exact_default);
+  (void)exact_default;
+  pl.fused = g_decode_tuning.warps_n != 1;
   // __launch_bounds__(128, MT == 2 ? 3 : (FUSED ? 4 : 5))
   pl.ctas_per_sm = pick(g_decode_tuning.warps_k, mrows > 8 ? 3 : (pl.fused ? 4 : 5));
   const int by_regs = pl.ctas_per_sm;

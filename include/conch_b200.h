@@ -180,9 +180,7 @@ CB200_API int cb200_scaled_gemm(const void* a, const void* b_t, const void* scal
 CB200_API int cb200_static_scaled_quant(const void* x, const void* scale, void* out, int64_t n, int in_dtype, int out_kind, void* stream);
 
 /* Debug/tuning knobs of the decode kernel (0 = heuristic).  Process-global, not thread-safe.
- *   warps_n   1: dequantise every weight before the MMA (W bits equal the reference's w_ref); 2: fused magic-number operands;
- *             0 (default): fused, except fp16 x int4 whose fused form scales activations by 1/16 in fp16 (that format's
- *             fast path is CB200_DECODE_STREAM)
+ *   warps_n   1: dequantise every weight before the MMA (W bits equal the reference's w_ref); 0/2: fused operands (default)
  *   warps_k   CTAs per SM assumed resident when the split count is chosen
  *   split_k   forced number of K slabs per 32-column block (rounded to a legal divisor)
  *   vec_words 1: element (2-byte) stores to the peers in cb200_mpgemm_push instead of 8-byte vectors (A/B measurements) */

@@ -187,9 +187,9 @@ def test_decode_tilings(scale_mode, units_per_warp):
 @pytest.mark.parametrize("scale", [2.0**-12, 1e-4, 1e-6])
 @pytest.mark.parametrize("variant", [_lib.AUTO, _lib.DECODE_MMA], ids=["auto", "decode_mma"])
 def test_default_decode_paths_keep_small_activations(scale, variant):
-    """the register-window kernel's fused fp16 x int4 form scales half of the activations by 1/16 in fp16 and loses
-    bits below 2^-10.  Neither default path does that any more: AUTO runs the streaming kernel (the 1/16 lands on an fp32
-    accumulator), and CB200_DECODE_MMA dequantises per weight for that format unless the fused form is asked for."""
+    """round 1's fused fp16 x int4 form scaled half of the activations by 1/16 in fp16 and lost bits below 2^-10.
+    Neither decode kernel does that any more: in both the x16 nibbles accumulate separately and the 1/16 lands on that fp32
+    accumulator when the scale group closes."""
     p = oracle.make_problem(4, 4096, 512, "uint4", 128, torch.float16, True, seed=21)
     xs = (p.x.float() * scale).to(torch.float16)
     x, wq, ws, wzp = to_cuda(xs, p.w_q_packed, p.w_s, p.w_zp)
@@ -521,7 +521,7 @@ def test_decode_group_sums_prologue(m, dtype, wname, zp, g):
     an all-ones MMA per operand pair.  One split forces 16..32 batches per warp, i.e. that path."""
     lib = _lib.load()
     try:
-        lib.cb200_set_decode_tuning(2, 0, 1, 0)  # (2: the fused operands, also for fp16 x int4 whose default is per-weight dequant)
+        lib.cb200_set_decode_tuning(2, 0, 1, 0)
         _run_case(m, 2048, 320, wname, g, dtype, zp, variant=_lib.DECODE_MMA)
         lib.cb200_set_decode_tuning(2, 0, 2, 0)
         _run_case(m, 4096, 192, wname, g, dtype, zp, variant=_lib.DECODE_MMA, zp_as=torch.uint8 if zp else None)
