@@ -205,13 +205,6 @@ def mixed_precision_gemm(
         # the reference honours arbitrary strides (gemm.py:518-525); the CUDA kernels want dense row-major
         x, w_q_packed, w_s = x.contiguous(), w_q_packed.contiguous(), w_s.contiguous()
         w_zp = None if w_zp is None else w_zp.contiguous()
-    # the kernels read with 16-byte vectors / TMA: a dense view that starts at an odd element of a bigger buffer is copied
-    # (the reference's Triton kernel accepts it as is)
-    if x.data_ptr() % 16:
-        x = x.clone()
-    if w_q_packed.data_ptr() % 16 or w_s.data_ptr() % 16 or (w_zp is not None and w_zp.numel() > 1 and w_zp.data_ptr() % 16):
-        w_q_packed, w_s = _dense_aligned(w_q_packed), _dense_aligned(w_s)
-        w_zp = None if w_zp is None else _dense_aligned(w_zp)
     if out is None:
         out = torch.empty((metadata.m_dim, metadata.n_dim), device=x.device, dtype=metadata.output_dtype)
     elif tuple(out.shape) != (metadata.m_dim, metadata.n_dim) or out.dtype != metadata.output_dtype or not out.is_contiguous():
@@ -222,9 +215,20 @@ def mixed_precision_gemm(
         bias = bias.contiguous()
     if metadata.m_dim == 0:
         return out
-    mixed_precision_gemm_launcher(
-        out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, bias=bias
-    )
+    try:
+        mixed_precision_gemm_launcher(
+            out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, bias=bias
+        )
+    except ValueError as e:
+        # the kernels read with 16-byte vectors / TMA: a dense view that starts at an odd element of a bigger buffer is copied
+        # and the call repeated (the reference's Triton kernel accepts it as is).  Checked here, on the failure path, so that the
+        # aligned case pays nothing for it.
+        if "16-byte aligned" not in str(e):
+            raise
+        mixed_precision_gemm_launcher(
+            out, _dense_aligned(x), _dense_aligned(w_q_packed), _dense_aligned(w_s), None if w_zp is None else _dense_aligned(w_zp),
+            metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, bias=bias,
+        )  # fmt: skip
     return out
 
 
