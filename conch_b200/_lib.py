@@ -35,6 +35,9 @@ EXPORTS = (
     "cb200_mpgemm_push",
     "cb200_mpgemm_push_signal",
     "cb200_wait_flags",
+    "cb200_mpgemm_chain",
+    "cb200_push",
+    "cb200_peer_copy",
     "cb200_last_variant",
     "cb200_last_launch_count",
     "cb200_dequantize",
@@ -98,6 +101,12 @@ def load() -> ctypes.CDLL:
         lib.cb200_mpgemm_push.argtypes = lib.cb200_mpgemm.argtypes + [ctypes.POINTER(c_void_p), c_int]  # peer_out, num_peers
         lib.cb200_mpgemm_push_signal.restype = c_int
         lib.cb200_mpgemm_push_signal.argtypes = lib.cb200_mpgemm_push.argtypes + [ctypes.POINTER(c_void_p), c_void_p]
+        lib.cb200_mpgemm_chain.restype = c_int
+        lib.cb200_mpgemm_chain.argtypes = lib.cb200_mpgemm_push_signal.argtypes + [c_void_p, c_int, c_void_p]  # x_flags, count, x_expected
+        lib.cb200_push.restype = c_int
+        lib.cb200_push.argtypes = [c_void_p, c_size_t, ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p]
+        lib.cb200_peer_copy.restype = c_int
+        lib.cb200_peer_copy.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
         lib.cb200_wait_flags.restype = c_int
         lib.cb200_wait_flags.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
         lib.cb200_dequantize.restype = c_int

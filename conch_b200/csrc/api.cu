@@ -209,7 +209,8 @@ int cb200_wait_flags(const void* flags, int count, void* expected, void* stream)
 static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M, int64_t K,
                       int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype, int out_dtype,
                       int zp_kind, int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant, void* stream,
-                      void* const* peer_out, int num_peers, void* const* peer_flags, void* local_flag, const void* bias) {
+                      void* const* peer_out, int num_peers, void* const* peer_flags, void* local_flag, const void* bias,
+                      const void* x_flags = nullptr, int x_flag_count = 0, void* x_expected = nullptr) {
   tls_last_variant = 0;
   tls_last_launches = 0;
   int rc = check_device();
@@ -266,6 +267,16 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
     }
     p.local_flag = reinterpret_cast<uint32_t*>(local_flag);
   }
+  if (x_flags != nullptr) {
+    if (!x_expected || x_flag_count < 1 || x_flag_count > 32 || (reinterpret_cast<uintptr_t>(x_flags) & 3u) ||
+        (reinterpret_cast<uintptr_t>(x_expected) & 3u)) {
+      set_error("cb200_mpgemm_chain: x_expected is null / misaligned or x_flag_count=%d outside 1..32", x_flag_count);
+      return CB200_ERR_ARG;
+    }
+    p.wait_flags = reinterpret_cast<const uint32_t*>(x_flags);
+    p.wait_expected = reinterpret_cast<uint32_t*>(x_expected);
+    p.wait_count = x_flag_count;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   int chosen = variant;
@@ -278,7 +289,9 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
       // (fused gather to 4 or more peers: the register-window kernel, whose column blocks finish -- and push -- at staggered
       //  times; the streaming kernel's CTAs all store in the same microsecond and the kernel then sits out a full NVLink
       //  round trip: measured 1.71-3.1 ms against 1.57 ms per 8-GPU step, profiles/r02_bench_n8*.json)
-      chosen = (decode && num_peers < 4 && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM : CB200_DECODE_MMA;
+      // (the in-kernel wait of cb200_mpgemm_chain exists in the streaming kernel only)
+      chosen = (decode && (num_peers < 4 || p.wait_flags != nullptr) && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM
+                                                                                                                          : CB200_DECODE_MMA;
     } else {
       chosen = CB200_TC_TS;
     }
@@ -290,6 +303,10 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
   }
   if (p.local_flag != nullptr && ((chosen != CB200_DECODE_MMA && chosen != CB200_DECODE_STREAM) || M > 16)) {
     set_error("cb200_mpgemm_push_signal: the completion flags are raised by the decode kernels only (M <= 16 in one pass)");
+    return CB200_ERR_UNSUPPORTED;
+  }
+  if (p.wait_flags != nullptr && chosen != CB200_DECODE_STREAM) {
+    set_error("cb200_mpgemm_chain: only the streaming decode kernel waits for its activations (M <= 16, fp16/bf16 x int4 or fp16 x int8)");
     return CB200_ERR_UNSUPPORTED;
   }
   int launches = 0;
@@ -328,6 +345,51 @@ int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* 
                              void* stream, void* const* peer_out, int num_peers, void* const* peer_flags, void* local_flag) {
   return run_mpgemm(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, weight_bias, group_size, act_dtype, out_dtype, zp_kind,
                     zp_is_scalar, workspace, workspace_bytes, variant, stream, peer_out, num_peers, peer_flags, local_flag, nullptr);
+}
+
+int cb200_mpgemm_chain(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out, int64_t M, int64_t K,
+                       int64_t N, int weight_size_bits, int weight_bias, int64_t group_size, int act_dtype, int out_dtype, int zp_kind,
+                       int zp_is_scalar, void* workspace, size_t workspace_bytes, int variant, void* stream, void* const* peer_out,
+                       int num_peers, void* const* peer_flags, void* local_flag, const void* x_flags, int x_flag_count,
+                       void* x_expected) {
+  return run_mpgemm(x, w_q_packed, w_s, w_zp, out, M, K, N, weight_size_bits, weight_bias, group_size, act_dtype, out_dtype, zp_kind,
+                    zp_is_scalar, workspace, workspace_bytes, variant, stream, peer_out, num_peers, peer_flags, local_flag, nullptr,
+                    x_flags, x_flag_count, x_expected);
+}
+
+int cb200_push(const void* src, size_t bytes, void* const* peer_dst, int num_peers, void* const* peer_flags, void* local_flag,
+               void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!src || !aligned16(src) || bytes == 0 || (bytes & 15u)) {
+    set_error("cb200_push: src must be 16-byte aligned and bytes a positive multiple of 16 (bytes=%zu)", bytes);
+    return CB200_ERR_ARG;
+  }
+  if (num_peers < 1 || num_peers > CB200_MAX_PEERS || !peer_dst || (local_flag && !peer_flags)) {
+    set_error("cb200_push: num_peers=%d out of range (1..%d) or null pointer array", num_peers, CB200_MAX_PEERS);
+    return CB200_ERR_ARG;
+  }
+  for (int i = 0; i < num_peers; ++i) {
+    if (!peer_dst[i] || !aligned16(peer_dst[i]) || (local_flag && (!peer_flags[i] || (reinterpret_cast<uintptr_t>(peer_flags[i]) & 3u)))) {
+      set_error("cb200_push: peer_dst[%d] null / not 16-byte aligned, or peer_flags[%d] null / misaligned", i, i);
+      return CB200_ERR_ARG;
+    }
+  }
+  if (local_flag && bytes > (size_t(1) << 20)) {
+    set_error("cb200_push: a signalled push is one CTA (decode-sized slices, <= 1 MiB); push %zu bytes without flags", bytes);
+    return CB200_ERR_UNSUPPORTED;
+  }
+  return launch_push(src, bytes, peer_dst, num_peers, peer_flags, local_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cb200_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) {
+    set_error("cb200_peer_copy: null pointer");
+    return CB200_ERR_ARG;
+  }
+  if (bytes == 0) return 0;
+  CB200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
 }
 
 int cb200_mpgemm_bias(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, const void* bias, void* out,

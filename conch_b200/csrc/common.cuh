@@ -33,6 +33,12 @@ struct Problem {
   // local_flag are incremented by one: per-GEMM visibility without a cross-GPU barrier, safe under CUDA-graph replay
   uint32_t* peer_flag[CB200_MAX_PEERS];
   uint32_t* local_flag;
+  // cb200_mpgemm_chain: x is itself a gathered buffer other GPUs push into -- it is complete once wait_flags[0 .. wait_count) have
+  // all reached *wait_expected + 1; the kernel's consumers spin on them (after griddepcontrol.wait, while the producer warp keeps
+  // filling the weight ring) and the grid's last block advances *wait_expected.  null: x belongs to the stream order.
+  const uint32_t* wait_flags;
+  uint32_t* wait_expected;
+  int wait_count;
   const void* out_bias;  // cb200_mpgemm_bias: [N] in the OUTPUT dtype, added to the fp32 sum before the one rounding (or null)
 };
 
@@ -47,16 +53,20 @@ __device__ __forceinline__ float bias_at(const Problem& p, int n) {
 // Called by a warp that has finished (stored and pushed) one 32-column block of a cb200_mpgemm_push_signal GEMV: system-scope
 // fence, count the block, and -- as the last block of the grid -- raise the flags.  `done` is a self-resetting counter.
 __device__ __forceinline__ void push_signal_block_done(const Problem& p, unsigned int* done, unsigned int total_blocks, int lane) {
-  if (p.local_flag == nullptr) return;
-  __threadfence_system();  // this warp's stores to the peers are performed system-wide before the count
+  if (p.local_flag == nullptr && p.wait_expected == nullptr) return;
+  if (p.local_flag != nullptr) __threadfence_system();  // this warp's stores to the peers are performed system-wide before the count
   __syncwarp();
   if (lane == 0) {
     const unsigned int prev = atomicAdd(done, 1u);
     if (prev == total_blocks - 1u) {
       *done = 0u;
-      __threadfence_system();
-      for (int i = 0; i < p.n_peers; ++i) atomicAdd_system(p.peer_flag[i], 1u);
-      atomicAdd_system(p.local_flag, 1u);
+      // cb200_mpgemm_chain: every block of the grid has finished, hence read *wait_expected: count this wait
+      if (p.wait_expected != nullptr) *p.wait_expected = *p.wait_expected + 1u;
+      if (p.local_flag != nullptr) {
+        __threadfence_system();
+        for (int i = 0; i < p.n_peers; ++i) atomicAdd_system(p.peer_flag[i], 1u);
+        atomicAdd_system(p.local_flag, 1u);
+      }
     }
   }
 }
@@ -90,6 +100,8 @@ int launch_scaled(const void* a, const void* b_t, const float* scale_a, const fl
                   int K, int N, int in_kind, int out_dtype, int sa_scalar, int sb_scalar, cudaStream_t stream);
 int launch_static_quant(const void* x, const float* scale, void* out, int64_t n, int in_dtype, int out_kind, cudaStream_t stream);
 int launch_wait_flags(const uint32_t* flags, int count, uint32_t* expected, cudaStream_t stream);
+int launch_push(const void* src, size_t bytes, void* const* peer_dst, int num_peers, void* const* peer_flags, void* local_flag,
+                cudaStream_t stream);
 struct StreamTuning {
   int ring_kb;   // shared memory the kernel may use per CTA, in KiB (0 = all of it)
   int ctas;      // upper bound on the CTAs launched (0 = one per SM)

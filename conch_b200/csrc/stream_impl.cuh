@@ -33,6 +33,8 @@ struct StreamGeom {
   int x_bytes;      // staged x slab
   int red_bytes;    // cluster reduction buffers + the group sums of x (at its end)
   int xsum_bytes;
+  int x_rot;        // staging of x: per-CTA rotation of the warps' 512-byte tasks (0 = none)
+  int win_stages;   // 16-row variant: stages of x staged at a time (the slab of x is windowed so that the weight ring keeps its depth)
   int no_hint;      // debug (cb200_set_stream_tuning ring_kb < 0): weight tiles without the L2 evict_first policy
   unsigned int* done;  // cb200_mpgemm_push_signal: self-resetting counter of finished 32-column slices (workspace), else unused
   long long* trace; // debug builds: [CTA][8] globaltimer stamps
@@ -328,31 +330,69 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
   constexpr int XR = 8 * MT;                           // rows of the sums table
   const uint32_t xsum = recv + geo.red_bytes - geo.xsum_bytes;  // [stage][scale row][XR] fp32: sums of x over the quads of a scale row
   asm volatile("griddepcontrol.wait;" ::: "memory");  // x, out and the peers belong to the stream order
+  const bool chained = p.wait_flags != nullptr;
+  if (chained) {
+    // cb200_mpgemm_chain: x is a gather buffer the other GPUs push into.  One warp spins until every rank's completion counter
+    // has reached this call's number (system-scope acquire), the rest of the consumers wait at the barrier; the producer warp is
+    // not involved -- the ring keeps filling with weights meanwhile.
+    if (warp == 0) {
+      uint32_t seen;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wait_expected) : "memory");
+      const uint32_t want = seen + 1u;
+      if (lane < p.wait_count) {
+        const uint32_t* f = p.wait_flags + lane;
+        for (unsigned spin = 0;; ++spin) {
+          uint32_t v;
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          if (int32_t(v - want) >= 0) break;
+          __nanosleep(64);
+          if (spin > (1u << 24)) __trap();  // a lost signal becomes a launch error (after seconds), not a hung GPU
+        }
+      }
+      __syncwarp();
+      asm volatile("fence.acq_rel.sys;" ::: "memory");  // one acquire for the whole warp's polls
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+  }
   RING_STAMP(1);
-  {  // stage this slab's activations (int4: every 8-k chunk permuted to the operand order) and sum them per (stage, scale row):
-     // consecutive lanes hold the chunks of one stage of one row -> a fixed shuffle tree, the same whatever M is
+  // Stage the activations of the stages [wi0, wi1) of this slab (int4: every 8-k chunk permuted to the operand order) and sum them
+  // per (stage, scale row): consecutive lanes hold the chunks of one stage of one row -> a fixed shuffle tree, the same whatever M
+  // is.  M <= 8: one window = the whole slab.  16 rows: windows of geo.win_stages stages -- a whole slab of 16 rows (128 KB at
+  // K = 4096) would leave the weight ring four stages, too few bytes in flight to cover the HBM latency.
+  auto stage_x = [&](int wi0, int wi1) {
     constexpr int CPS = 4 * F::CPQ;              // chunks per stage and row
-    const int cpr = nstages * CPS;               // chunks per row, counted from the aligned start qa0
-    const int c_lo = (q_lo - qa0) * F::CPQ, c_hi = (q_hi - qa0) * F::CPQ;
+    const int cw0 = wi0 * CPS;                   // first chunk of the window, counted from the aligned start qa0
+    const int cpr = (wi1 - wi0) * CPS;           // chunks per row in the window
+    const int c_lo = max((q_lo - qa0) * F::CPQ, cw0), c_hi = (q_hi - qa0) * F::CPQ;
     const int esh = (BITS == 4 ? 2 : 1) + mshift;  // chunks per scale row = 1 << esh
+    const int e0 = wi0 * geo.gps;                  // first entry of the sums table in the window
     const char* xg = reinterpret_cast<const char*>(p.x) + size_t(qa0) * F::XQ;
-    constexpr int XU = 4;  // loads in flight per thread
-    for (int base0 = threadIdx.x & ~31; base0 < M * cpr; base0 += XU * nthr) {
+    constexpr int XU = MT == 1 ? 4 : 8;  // loads in flight per thread
+    // Every CTA reads the same rows of x at the same moment -- a broadcast the L2 serves line by line.  The warps' 512-byte tasks are
+    // therefore rotated by a per-CTA offset (geo.x_rot tasks per CTA), so that at any instant the CTAs ask for different lines.
+    const int ntask = (M * cpr + 31) >> 5, nwc = nthr >> 5;
+    const int rot = geo.x_rot ? int((unsigned(blockIdx.y * gridDim.x + blockIdx.x) * unsigned(geo.x_rot)) % unsigned(ntask)) : 0;
+    for (int task0 = warp; task0 < ntask; task0 += XU * nwc) {
       uint4 v[XU];
       int mm[XU], cv[XU];
       bool ok[XU];
 #pragma unroll
       for (int u = 0; u < XU; ++u) {
-        const int idx = base0 + u * nthr + lane;
+        int tr = task0 + u * nwc + rot;
+        if (tr >= ntask) tr -= ntask;
+        const int idx = tr * 32 + lane;
         mm[u] = idx / cpr;
-        cv[u] = idx - mm[u] * cpr;
+        cv[u] = cw0 + idx - mm[u] * cpr;
         ok[u] = idx < M * cpr && cv[u] >= c_lo && cv[u] < c_hi;
         v[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(xg + size_t(mm[u]) * p.K * 2) + cv[u]);
+        if (ok[u]) {  // (a pushed-into x is read past L1: these lines were written by other GPUs while this kernel was resident)
+          const uint4* src = reinterpret_cast<const uint4*>(xg + size_t(mm[u]) * p.K * 2) + cv[u];
+          v[u] = chained ? __ldcg(src) : __ldg(src);
+        }
       }
 #pragma unroll
       for (int u = 0; u < XU; ++u) {
-        if (base0 + u * nthr >= M * cpr) break;  // (warp-uniform)
+        if (task0 + u * nwc >= ntask) break;  // (warp-uniform)
         float sum = 0.f;
         if (ok[u]) {
           uint4 o = v[u];
@@ -376,13 +416,12 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
         if (esh > 1) sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         if (esh > 2) sum += __shfl_xor_sync(0xffffffffu, sum, 4);
         if (esh > 3) sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-        if (base0 + u * nthr + lane < M * cpr && (cv[u] & ((1 << esh) - 1)) == 0)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + ((cv[u] >> esh) * XR + mm[u]) * 4), "f"(sum) : "memory");
+        if (mm[u] < M && (cv[u] & ((1 << esh) - 1)) == 0)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + (((cv[u] >> esh) - e0) * XR + mm[u]) * 4), "f"(sum) : "memory");
       }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
-  }
-  RING_STAMP(2);
+  };
 
   float acc[MT][2][4];
   Accum<MT, HAS_Q> qa;
@@ -401,14 +440,18 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
   for (int i = 0; i < 4; ++i) sa[i] = sb[i] = 0.f;
   const uint32_t lane_w0 = wl * 2048 + t * 128 + (uint32_t(ch ^ t) << 4);      // quads 0 / 2 of a stage: + 0 / + 1024
   const uint32_t lane_w1 = wl * 2048 + t * 128 + (uint32_t(ch ^ t ^ 4) << 4);  // quads 1 / 3: + 512 / + 1536
-  uint32_t lane_x[MT];                                                         // + quad * XQ
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    const int m = 8 * mt + gq;
-    lane_x[mt] = xs + (m < M ? m : 0) * geo.x_pitch + t * (F::XQ / 4) - q_lo * F::XQ;
-  }
+  uint32_t lane_x[MT];                                                         // + quad * XQ (set per window of x)
   const uint32_t lane_s = s_off + (wl * 32 + ch * 4) * 2, lane_z = z_off + (wl * 32 + ch * 4) * geo.zes;
-  const uint32_t lane_xs = xsum + 8 * t;  // + entry * XR * 4 (+ 32 for the second row tile): X[m = 2t], X[m = 2t + 1]
+  uint32_t lane_xs = xsum + 8 * t;  // + entry * XR * 4 (+ 32 for the second row tile): X[m = 2t], X[m = 2t + 1] (per window)
+  auto enter_window = [&](int wi0) {  // x and its sums are addressed by absolute quad / stage: rebase them on the staged window
+    const int qbase = max(q_lo, qa0 + 4 * wi0);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int m = 8 * mt + gq;
+      lane_x[mt] = xs + (m < M ? m : 0) * geo.x_pitch + t * (F::XQ / 4) - qbase * F::XQ;
+    }
+    lane_xs = xsum + 8 * t - uint32_t(wi0 * geo.gps) * (XR * 4);
+  };
   const float fbias = float(p.bias);
   float zscalar = 0.f;
   if (p.zp_kind != CB200_ZP_NONE && p.zp_scalar) {  // one zero-point for the whole matrix: fetch it once
@@ -541,6 +584,14 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
 
   const int i_full0 = q_lo > qa0 ? 1 : 0, i_full1 = (q_hi - qa0) >> 2;  // stages [i_full0, i_full1) lie wholly inside the slab
   int i = grp;
+  const int wst = MT == 1 ? nstages : geo.win_stages;  // (M <= 8: one window)
+  for (int wi0 = 0; wi0 < nstages; wi0 += wst) {
+  const int wi1 = min(nstages, wi0 + wst);
+  if (MT > 1 && wi0 > 0) asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");  // every warp is done with the previous window of x
+  stage_x(wi0, wi1);
+  enter_window(wi0);
+  if (wi0 == 0) RING_STAMP(2);
+  const int w_full1 = min(i_full1, wi1);
   if (mshift == 2) {
     if (i < i_full0) {
       generic_stage(i);
@@ -552,7 +603,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
         if (active) close_group();
         open = false;
       }
-      for (; i < i_full1; i += NGRP) {
+      for (; i < w_full1; i += NGRP) {
         const uint32_t st = stages + slot * geo.stage_bytes;
         mbar_wait(bar_full + 8 * slot, phase);
         if (i == grp) RING_STAMP(3);
@@ -579,7 +630,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
       }
     } else {
       // ---- scale groups span several stages (larger groups, per-channel) ------------------------------------------------
-      for (; i < i_full1; i += NGRP) {
+      for (; i < w_full1; i += NGRP) {
         const uint32_t st = stages + slot * geo.stage_bytes;
         mbar_wait(bar_full + 8 * slot, phase);
         if (i == grp) RING_STAMP(3);
@@ -608,10 +659,12 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
         advance();
       }
     }
-    for (; i < nstages; i += NGRP) generic_stage(i);  // an unaligned last stage
+    if (wi1 > i_full1)
+      for (; i < wi1; i += NGRP) generic_stage(i);  // an unaligned last stage
   } else {
-    for (; i < nstages; i += NGRP) generic_stage(i);
+    for (; i < wi1; i += NGRP) generic_stage(i);
   }
+  }  // windows of x
   if (open && active) close_group();
   RING_STAMP(4);
 

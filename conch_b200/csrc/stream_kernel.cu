@@ -29,6 +29,8 @@
 #include <atomic>
 
 #include "host_util.cuh"
+#include <cstdlib>
+
 #include "stream_impl.cuh"
 
 namespace cb200 {
@@ -39,7 +41,7 @@ long long* g_stream_trace = nullptr;
 struct StreamPlan {
   int nw, S, ngrp, ring;
   int pf, QPB, qpg, one_group, gps, zes;
-  int stage_bytes, x_pitch, x_bytes, red_bytes, xsum_bytes;
+  int stage_bytes, x_pitch, x_bytes, red_bytes, xsum_bytes, win_stages;
   size_t smem;
   dim3 grid;
 };
@@ -97,9 +99,18 @@ static StreamPlan stream_plan(int mrows, int K, int N, int bits, int g, int zp_k
   pl.stage_bytes = ((2048 * pl.nw + pl.gps * BN * (2 + pl.zes) + 1023) / 1024) * 1024;
   const int nxq = (pl.QPB + pl.S - 1) / pl.S + 1;  // quads of the longest slab
   const int xq = 4 * pl.pf * 2;                    // bytes of one x row per quad
-  pl.x_pitch = nxq * xq + ((nxq * xq) % 128 == 0 ? 64 : 0);
-  pl.x_bytes = mrows * pl.x_pitch;
   const int nstages = (nxq + 3) / 4 + 1;
+  // 16-row variant: x is staged in windows of win_stages stages (<= 64 KB), so that the ring keeps its depth
+  pl.win_stages = nstages;
+  if (mrows > 8 && mrows * nxq * xq > 64 * 1024) {
+    pl.win_stages = (64 * 1024) / (mrows * 4 * xq);
+    if (pl.win_stages < 2) pl.win_stages = 2;
+    const int nwin = (nstages + pl.win_stages - 1) / pl.win_stages;
+    pl.win_stages = (nstages + nwin - 1) / nwin;  // even windows
+  }
+  const int wxq = pl.win_stages < nstages ? 4 * pl.win_stages : nxq;  // quads of x staged at a time
+  pl.x_pitch = wxq * xq + ((wxq * xq) % 128 == 0 ? 64 : 0);
+  pl.x_bytes = mrows * pl.x_pitch;
   pl.xsum_bytes = nstages * pl.gps * (mrows > 8 ? 64 : 32);
   pl.red_bytes = ((pl.nw + pl.S - 1) / pl.S) * pl.S * pl.ngrp * mrows * 128 + pl.xsum_bytes;
   const int budget = (g_stream_tuning.ring_kb > 0 ? g_stream_tuning.ring_kb : 224) * 1024;
@@ -162,9 +173,13 @@ static int stream_tmap(const Problem& p, int pf, int nw, const CUtensorMap** out
 }
 
 int launch_stream(const Problem& p_in, int bits, int act_dtype, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches) {
-  if (p_in.local_flag != nullptr && (ws == nullptr || ws_bytes < size_t(CB200_WORKSPACE_COUNTER_BYTES))) {
-    set_error("cb200_mpgemm_push_signal needs the %d-byte counter area of the workspace", CB200_WORKSPACE_COUNTER_BYTES);
+  if ((p_in.local_flag != nullptr || p_in.wait_flags != nullptr) && (ws == nullptr || ws_bytes < size_t(CB200_WORKSPACE_COUNTER_BYTES))) {
+    set_error("cb200_mpgemm_push_signal / cb200_mpgemm_chain need the %d-byte counter area of the workspace", CB200_WORKSPACE_COUNTER_BYTES);
     return CB200_ERR_WORKSPACE;
+  }
+  if (p_in.wait_flags != nullptr && p_in.M > 16) {
+    set_error("cb200_mpgemm_chain: one pass of the decode kernel (M <= 16)");
+    return CB200_ERR_UNSUPPORTED;
   }
   if (size_t(p_in.K / p_in.g) * p_in.N >= (size_t(1) << 31)) {
     set_error("scale matrix too large");
@@ -204,6 +219,14 @@ int launch_stream(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     geo.x_bytes = pl.x_bytes;
     geo.red_bytes = pl.red_bytes;
     geo.xsum_bytes = pl.xsum_bytes;
+    geo.win_stages = pl.win_stages;
+    {
+      static const int x_rot_env = [] {
+        const char* e = getenv("CB200_STREAM_XROT");  // A/B knob of the x-staging rotation (tasks per CTA; default below)
+        return e ? atoi(e) : -1;
+      }();
+      geo.x_rot = x_rot_env >= 0 ? x_rot_env : 0;
+    }
     geo.done = ws ? reinterpret_cast<unsigned int*>(ws) + (CB200_WORKSPACE_COUNTER_BYTES / 4 - 1) : nullptr;
     geo.no_hint = g_stream_tuning.dbg & 1;
     geo.trace = g_stream_trace;

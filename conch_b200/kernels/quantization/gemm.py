@@ -126,13 +126,17 @@ def mixed_precision_gemm_launcher(
     variant: int = _lib.AUTO,
     peer_out_ptrs: Sequence[int] | None = None,
     signal: tuple[Sequence[int], int] | None = None,
+    x_ready: tuple[int, int, int] | None = None,
     bias: torch.Tensor | None = None,
 ) -> None:
     """Enqueue out = x @ dequant(W) (+ bias) on the current CUDA stream.  Never synchronises.
 
     Counterpart of the reference launcher (conch/kernels/quantization/gemm.py:482-545): same argument order.
     `peer_out_ptrs` (multi-GPU, decode regime): device pointers of other GPUs' [M, N] buffers the kernel's epilogue also
-    stores the result to (`cb200_mpgemm_push`, see conch_b200/sharded.py).
+    stores the result to (`cb200_mpgemm_push`, see conch_b200/sharded.py).  `signal` = (peer flag pointers, local flag pointer):
+    completion counters raised once everything is pushed (`cb200_mpgemm_push_signal`).  `x_ready` = (flags pointer, count,
+    expected pointer): `x` is a gather buffer that is complete once those counters have been raised -- the kernel itself waits
+    (`cb200_mpgemm_chain`).
     """
     lib = _lib.load()
     device = x.device
@@ -169,20 +173,23 @@ def mixed_precision_gemm_launcher(
     entry = lib.cb200_mpgemm
     ws_at = 15  # position of the workspace pointer in `args`
     if bias is not None:
-        if peer_out_ptrs or signal is not None:
+        if peer_out_ptrs or signal is not None or x_ready is not None:
             raise NotImplementedError("bias and the multi-GPU push epilogue cannot be combined")
         entry = lib.cb200_mpgemm_bias  # (..., w_zp, bias, out, ...)
         args = args[:4] + (bias.data_ptr(),) + args[4:]
         ws_at = 16
-    if peer_out_ptrs or signal is not None:
+    if peer_out_ptrs or signal is not None or x_ready is not None:
         peers = list(peer_out_ptrs or ())
         entry = lib.cb200_mpgemm_push
         args = args + ((ctypes.c_void_p * max(len(peers), 1))(*peers), len(peers))
-        if signal is not None:
+        if signal is not None or x_ready is not None:
             # (peer flag pointers, local flag pointer): the kernel bumps the counters once the whole result is pushed
-            peer_flags, local_flag = signal
+            peer_flags, local_flag = signal if signal is not None else ((), None)
             entry = lib.cb200_mpgemm_push_signal
             args = args + ((ctypes.c_void_p * max(len(peer_flags), 1))(*peer_flags), local_flag)
+        if x_ready is not None:
+            entry = lib.cb200_mpgemm_chain
+            args = args + tuple(x_ready)
     if index != torch.cuda.current_device():
         with torch.cuda.device(device):
             rc = entry(*args)

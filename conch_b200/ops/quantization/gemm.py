@@ -183,6 +183,7 @@ def mixed_precision_gemm(
     out: torch.Tensor | None = None,
     peer_out_ptrs: Sequence[int] | None = None,
     signal: tuple[Sequence[int], int] | None = None,
+    x_ready: tuple[int, int, int] | None = None,
     bias: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """Mixed precision GEMM: `x[M,K] @ dequant(w_q_packed[K/pf,N], w_s, w_zp) -> [M,N]`.
@@ -190,7 +191,9 @@ def mixed_precision_gemm(
     Signature of the reference op (conch/ops/quantization/gemm.py:133-147) plus optional keywords:
     `variant` forces a kernel family (debug / benchmarking), `out` reuses a caller-owned output buffer, `peer_out_ptrs`
     (multi-GPU, decode regime: M <= 8) lists peer-GPU buffers the kernel also stores the result to, `signal` = (peer flag
-    pointers, local flag pointer) makes it bump completion counters on every GPU afterwards (conch_b200/sharded.py), and
+    pointers, local flag pointer) makes it bump completion counters on every GPU afterwards (conch_b200/sharded.py), `x_ready` =
+    (flags pointer, count, expected pointer) declares `x` a gather buffer other GPUs push into, complete once those counters have
+    been raised -- the kernel waits for them itself while its weights stream in (`cb200_mpgemm_chain`) -- and
     `bias` ([N], output dtype) is added in the kernels' epilogue -- to the fp32 sum, before the one rounding -- instead of by
     the separate `output.add_(bias)` kernel a caller of the reference op runs (the reference's sibling op does exactly that,
     conch/ops/quantization/gemm.py:249-250).
@@ -217,7 +220,7 @@ def mixed_precision_gemm(
         return out
     try:
         mixed_precision_gemm_launcher(
-            out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, bias=bias
+            out, x, w_q_packed, w_s, w_zp, metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, x_ready=x_ready, bias=bias
         )
     except ValueError as e:
         # the kernels read with 16-byte vectors / TMA: a dense view that starts at an odd element of a bigger buffer is copied
@@ -227,7 +230,7 @@ def mixed_precision_gemm(
             raise
         mixed_precision_gemm_launcher(
             out, _dense_aligned(x), _dense_aligned(w_q_packed), _dense_aligned(w_s), None if w_zp is None else _dense_aligned(w_zp),
-            metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, bias=bias,
+            metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, x_ready=x_ready, bias=bias,
         )  # fmt: skip
     return out
 

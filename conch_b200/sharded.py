@@ -93,12 +93,12 @@ class ShardedMixedPrecisionLinear:
         return self._gather_buf.view(self.world, m, self.n_local), work
 
     # ---- fused gather: the GEMM kernel's own epilogue stores into every rank's gather buffer (P2P over NVLink) ----------
-    PUSH_MAX_ROWS = 8  # the decode kernel is what AUTO picks up to here for every shape (cb200_mpgemm_push is decode-only)
+    PUSH_MAX_ROWS = 8  # the decode kernels are what AUTO picks up to here for every shape (cb200_mpgemm_push is decode-only)
 
-    def _symmetric(self, m: int, dtype: torch.dtype, device: torch.device):
+    def _symmetric(self, m: int, dtype: torch.dtype, device: torch.device, key=None):
         """`[G, M, N/G]` gather buffer in symmetric memory (every rank maps every rank's copy), allocated once per (M, dtype).
         COLLECTIVE on first use: all ranks must call with the same M and dtype."""
-        key = (m, dtype)
+        key = key or (m, dtype)
         if key not in self._symm:
             import torch.distributed._symmetric_memory as symm_mem
 
@@ -124,7 +124,96 @@ class ShardedMixedPrecisionLinear:
             self._flags = (flags, hdl, peer_flags)
         return self._flags
 
-    def pushed_signalled(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
+    # ---- side streams (per device, shared by all layers): the decoupled push and the copy-engine gather run there --------
+    _side: dict[int, "torch.cuda.Stream"] = {}
+    _peer_streams: dict[int, list["torch.cuda.Stream"]] = {}
+
+    @classmethod
+    def _side_stream(cls, device: torch.device) -> "torch.cuda.Stream":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in cls._side:
+            cls._side[idx] = torch.cuda.Stream(device=device)
+        return cls._side[idx]
+
+    def pushed_async(self, x: torch.Tensor, *, signalled: bool = True, **kwargs) -> torch.Tensor:
+        """The DECOUPLED form of `pushed_signalled()`: the GEMV stores only this rank's slot (the plain single-GPU kernel, at
+        single-GPU speed) and a `cb200_push` kernel on a side stream then copies the slot to every peer with 16-byte P2P stores
+        and raises the same completion counters.  The token's GEMV chain therefore never contains a kernel with outstanding
+        NVLink stores -- a grid that wrote to peers is not complete, and the next kernel's `griddepcontrol.wait` does not
+        return, before the remote stores are acknowledged -- while every GEMV's gathered output still becomes visible on its
+        own (`wait()`).  `join()` makes the current stream wait for all pushes enqueued so far (end of a token / of a graph
+        capture)."""
+        m = x.shape[0]
+        if self.world == 1:
+            return self.local(x, **kwargs).unsqueeze(0)
+        out_dtype = kwargs.get("output_dtype") or x.dtype
+        buf, _, peers = self._symmetric(m, out_dtype, x.device)
+        self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size, out=buf[self.rank], **kwargs)
+        import ctypes
+
+        from conch_b200 import _lib
+
+        side = self._side_stream(x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))  # fork: the push depends on THIS GEMV only
+        nbytes = m * self.n_local * buf.element_size()
+        peer_arr = (ctypes.c_void_p * len(peers))(*peers)
+        if signalled:
+            flags, _, peer_flags = self._flag_array(x.device)
+            flag_arr = (ctypes.c_void_p * len(peer_flags))(*peer_flags)
+            local_flag = flags.data_ptr() + 4 * self.rank
+        else:
+            flag_arr, local_flag = None, None
+        with torch.cuda.device(x.device):
+            _lib.raise_for_status(_lib.load().cb200_push(buf[self.rank].data_ptr(), nbytes, peer_arr, len(peers), flag_arr, local_flag,
+                                                         side.cuda_stream))  # fmt: skip
+        return buf
+
+    @classmethod
+    def join(cls, device: torch.device) -> None:
+        """The current stream waits for every side-stream push enqueued so far on `device`."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx in cls._side:
+            torch.cuda.current_stream(device).wait_stream(cls._side[idx])
+
+    def gathered_ce_async(self, x: torch.Tensor, slot: int = 0, **kwargs) -> tuple[torch.Tensor, "torch.cuda.Event | None"]:
+        """Large-M all-gather on the COPY ENGINES: the GEMM writes this rank's `[M, N/G]` slice straight into its slot of a
+        symmetric `[G, M, N/G]` buffer, then one `cudaMemcpyAsync` per peer (each on its own side stream, so the copies run on
+        different engines at once) stores the slice into the same slot of that peer's buffer, and a device-side barrier across
+        the ranks closes the gather.  No SM is involved, so -- unlike an NCCL kernel, which cannot become resident while the next
+        GEMM's one-CTA-per-SM grid holds the shared memory -- the transfer really overlaps the next GEMM.  Returns the buffer
+        (two of them alternate: `slot` 0 / 1) and an event; `current_stream().wait_event(event)` before reading the peers'
+        slots, and before the call after next on the same slot may overwrite the local one."""
+        y_shape = (x.shape[0], self.n_local)
+        out_dtype = kwargs.get("output_dtype") or x.dtype
+        if self.world == 1:
+            return self.local(x, **kwargs).unsqueeze(0), None
+        key = (("ce", slot, y_shape[0]), out_dtype)
+        buf, hdl, peers = self._symmetric(y_shape[0], out_dtype, x.device, key=key)
+        self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size, out=buf[self.rank], **kwargs)
+        from conch_b200 import _lib
+
+        lib = _lib.load()
+        idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        streams = self._peer_streams.setdefault(idx, [])
+        while len(streams) < len(peers):
+            streams.append(torch.cuda.Stream(device=x.device))
+        cur = torch.cuda.current_stream(x.device)
+        side = self._side_stream(x.device)
+        nbytes = y_shape[0] * self.n_local * buf.element_size()
+        src = buf[self.rank].data_ptr()
+        with torch.cuda.device(x.device):
+            for st, dst in zip(streams, peers):
+                st.wait_stream(cur)
+                _lib.raise_for_status(lib.cb200_peer_copy(dst, src, nbytes, st.cuda_stream))
+            for st in streams[: len(peers)]:
+                side.wait_stream(st)
+            with torch.cuda.stream(side):
+                hdl.barrier(channel=2 + slot)  # every rank's copies have landed everywhere
+                done = torch.cuda.Event()
+                done.record(side)
+        return buf, done
+
+    def pushed_signalled(self, x: torch.Tensor, *, after: "ShardedMixedPrecisionLinear | None" = None, **kwargs) -> torch.Tensor:
         """`pushed()` with PER-GEMM visibility and no cross-GPU barrier: when the whole `[M, N/G]` slice has reached every rank,
         the kernel raises this rank's completion flag on every GPU (`cb200_mpgemm_push_signal`).  `wait()` then blocks the
         CURRENT STREAM (not the host) until all ranks' flags of this call have arrived: the gathered `[G, M, N/G]` buffer is
@@ -137,6 +226,12 @@ class ShardedMixedPrecisionLinear:
         out_dtype = kwargs.get("output_dtype") or x.dtype
         buf, _, peers = self._symmetric(m, out_dtype, x.device)
         flags, _, peer_flags = self._flag_array(x.device)
+        if after is not None:
+            # `x` is (derived from) `after`'s gathered output: the kernel itself waits for all ranks' completion counters of
+            # `after`'s latest pushed_signalled() -- cb200_mpgemm_chain -- instead of a wait() kernel in between.  One chained
+            # consumer per signalled producer (they share `after`'s wait counter).
+            aflags = after._flag_array(x.device)[0]
+            kwargs["x_ready"] = (aflags.data_ptr(), self.world, aflags.data_ptr() + 4 * max(self.world, 8))
         self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size, out=buf[self.rank],
                    peer_out_ptrs=peers, signal=(peer_flags, flags.data_ptr() + 4 * self.rank), **kwargs)  # fmt: skip
         return buf

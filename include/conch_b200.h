@@ -145,6 +145,37 @@ CB200_API int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, co
  * (count <= 32). */
 CB200_API int cb200_wait_flags(const void* flags, int count, void* expected, void* stream);
 
+/* cb200_mpgemm_push_signal whose ACTIVATIONS are themselves a gathered buffer that other GPUs push into (the all-gather -> GEMM
+ * side of an N-sharded chain: gate_up -> gather -> down -> gather ...).  x is complete once x_flags[0 .. x_flag_count) (the
+ * completion counters the producing cb200_mpgemm_push_signal / cb200_push calls raise on this GPU) have all reached
+ * *x_expected + 1.  The WAIT HAPPENS INSIDE THE KERNEL: its consumer warps spin on the counters while the producer warp already
+ * fills the shared-memory ring with this GEMV's weights, so the NVLink latency of the previous GEMV's push overlaps this one's
+ * prologue -- no wait kernel, no barrier, no NCCL.  The grid's last block advances *x_expected (device memory, zero-initialised),
+ * so one chained call per signalled producer is safe under CUDA-graph replay.  Streaming decode kernel only (M <= 16; AUTO
+ * selects it).  peer_out / peer_flags / local_flag as in cb200_mpgemm_push_signal (num_peers == 0 and local_flag == NULL: the
+ * result stays local).  x_flags == NULL: plain cb200_mpgemm_push_signal. */
+CB200_API int cb200_mpgemm_chain(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
+                 int64_t M, int64_t K, int64_t N,
+                 int weight_size_bits, int weight_bias, int64_t group_size,
+                 int act_dtype, int out_dtype, int zp_kind, int zp_is_scalar,
+                 void* workspace, size_t workspace_bytes,
+                 int variant, void* stream, void* const* peer_out, int num_peers,
+                 void* const* peer_flags, void* local_flag,
+                 const void* x_flags, int x_flag_count, void* x_expected);
+
+/* The gather WITHOUT the GEMM: copy `bytes` (a multiple of 16) from src to peer_dst[0 .. num_peers) with 16-byte P2P stores and
+ * -- when local_flag != NULL -- raise the same completion counters as cb200_mpgemm_push_signal once everything has been stored.
+ * Meant for a SIDE stream: the kernel uses no shared memory and becomes resident next to the decode kernel of the main stream,
+ * so a token's GEMV chain contains no kernel with outstanding NVLink stores (a grid is not complete, and its dependents are
+ * not released, before its remote stores are acknowledged).  A signalled push is one CTA (<= 1 MiB). */
+CB200_API int cb200_push(const void* src, size_t bytes, void* const* peer_dst, int num_peers,
+                 void* const* peer_flags, void* local_flag, void* stream);
+
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): the copy-engine leg of the large-M all-gather -- every rank
+ * copies its [M, N/G] slice into its slot of every peer's buffer from per-peer side streams while the next GEMM owns the SMs
+ * (conch_b200/sharded.py gathered_ce_async). */
+CB200_API int cb200_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+
 /* Which kernel family the last cb200_mpgemm call on this thread dispatched to (a cb200_variant), and how many
  * kernel launches it enqueued.  Used by tests and by bench.py's `gpu_launches` accounting. */
 CB200_API int cb200_last_variant(void);

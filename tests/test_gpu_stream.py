@@ -257,6 +257,78 @@ def test_push_epilogue_writes_every_peer_buffer():
     assert_gemm_close(out, oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, 4, 0, 128))
 
 
+def test_chain_waits_inside_the_kernel_for_its_activations():
+    """cb200_mpgemm_chain: x is a gather buffer "another GPU" fills (here: a second stream of the same GPU).  The GEMV is enqueued
+    FIRST, its consumers spin on the completion counters while the ring fills; the writer then stores x and raises the counters
+    (cb200_push with flags, the same counters a pushing GEMV raises).  The result must be computed from the NEW x, the wait's own
+    count advances by one per call, and the pair replays."""
+    import ctypes
+
+    lib = _lib.load()
+    p = oracle.make_problem(2, 2048, 512, "uint4", 128, torch.float16, True, seed=5)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    want = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, variant=STREAM)
+    xbuf = torch.zeros_like(x)  # the "gather buffer": starts with stale contents
+    flags = torch.zeros(16, dtype=torch.int32, device="cuda")  # [0..1]: counters of two "ranks"; [8]: the chained kernel's own count
+    out = torch.empty_like(want)
+    writer, main = torch.cuda.Stream(), torch.cuda.Stream()
+    # Every kernel the writer will launch is loaded BEFORE a GEMV spins: loading a module (CUDA lazy loading) while a kernel that
+    # cannot finish is resident ends in a launch failure (measured: profiles/r02_chain_debug.log).
+    with torch.cuda.stream(writer):
+        torch.cuda._sleep(1000)
+        scratch = torch.zeros_like(x)
+        _lib.raise_for_status(lib.cb200_push(x.data_ptr(), x.numel() * 2, (ctypes.c_void_p * 1)(scratch.data_ptr()), 1, None, None,
+                                             writer.cuda_stream))  # fmt: skip
+    torch.cuda.synchronize()
+    for rep in range(1, 4):
+        xbuf.zero_()
+        out.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(main):
+            mixed_precision_gemm(xbuf, wq, ws, wzp, 4, 0, 128, out=out, x_ready=(flags.data_ptr(), 2, flags.data_ptr() + 32))
+        assert lib.cb200_last_variant() == STREAM  # AUTO picks the kernel that can wait
+        with torch.cuda.stream(writer):
+            torch.cuda._sleep(2_000_000)  # the GEMV is resident and spinning by now
+            peer = (ctypes.c_void_p * 1)(xbuf.data_ptr())
+            pflag = (ctypes.c_void_p * 1)(flags.data_ptr() + 4)
+            _lib.raise_for_status(lib.cb200_push(x.data_ptr(), x.numel() * 2, peer, 1, pflag, flags.data_ptr(), writer.cuda_stream))
+        torch.cuda.synchronize()
+        assert flags[:2].tolist() == [rep, rep] and int(flags[8]) == rep
+        assert torch.equal(bits(out), bits(want))
+    with pytest.raises(NotImplementedError):  # only the streaming kernel waits
+        mixed_precision_gemm(xbuf, wq, ws, wzp, 4, 0, 128, out=out, variant=_lib.DECODE_MMA, x_ready=(flags.data_ptr(), 2, flags.data_ptr() + 32))
+    with pytest.raises(ValueError):
+        mixed_precision_gemm(xbuf, wq, ws, wzp, 4, 0, 128, out=out, x_ready=(flags.data_ptr(), 40, flags.data_ptr() + 32))
+
+
+def test_push_kernel_copies_to_every_peer_and_counts():
+    """cb200_push: the gather without the GEMM (side-stream form of the fused push)."""
+    import ctypes
+
+    lib = _lib.load()
+    for nbytes, signalled in ((57344, True), (16, True), (3 << 20, False)):
+        src = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, device="cuda")
+        peers = [torch.zeros_like(src) for _ in range(7)]
+        flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+        parr = (ctypes.c_void_p * 7)(*[t.data_ptr() for t in peers])
+        farr = (ctypes.c_void_p * 7)(*[flags.data_ptr() + 4 * (i + 1) for i in range(7)]) if signalled else None
+        stream = torch.cuda.current_stream().cuda_stream
+        for rep in range(2):
+            _lib.raise_for_status(lib.cb200_push(src.data_ptr(), nbytes, parr, 7, farr, flags.data_ptr() if signalled else None, stream))
+        torch.cuda.synchronize()
+        for t in peers:
+            assert torch.equal(t, src)
+        assert flags.tolist() == ([2] * 8 if signalled else [0] * 8)
+    with pytest.raises(ValueError):
+        _lib.raise_for_status(lib.cb200_push(src.data_ptr(), 24, parr, 7, None, None, stream))  # not a multiple of 16
+    with pytest.raises(NotImplementedError):
+        _lib.raise_for_status(lib.cb200_push(src.data_ptr(), 3 << 20, parr, 7, farr or parr, flags.data_ptr(), stream))  # signalled: <= 1 MiB
+    dst = torch.zeros_like(src)
+    _lib.raise_for_status(lib.cb200_peer_copy(dst.data_ptr(), src.data_ptr(), src.numel(), stream))
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src)
+
+
 def test_dequant_still_bit_exact_next_to_it():
     p = oracle.make_problem(1, 1024, 256, "uint4", 128, torch.float16, True, seed=1)
     wq, ws, wzp = to_cuda(p.w_q_packed, p.w_s, p.w_zp)
