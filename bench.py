@@ -20,7 +20,7 @@ step streams its weights from HBM).  A "step" is one such token.
 Multi-GPU (N > 1): the headline line is weak-scaled -- every rank owns an equally sized column (N) shard of an N-times wider
 layer, runs the same per-GPU step, and the outputs of every GEMV are gathered on every rank (fused into the kernel's epilogue).
 Next to it, `config5_70b_ffn` reports BASELINE config 5 -- the Llama-3-70B FFN (K=8192, N=28672) column-sharded over the N GPUs,
-STRONG scaling, at M=1 (fused gather) and M=4096 (NCCL all-gather overlapped with the next GEMM): compute / gather / end to end.
+STRONG scaling, at M=1 (fused gather) and M=4096 (multicast push overlapped with the next GEMM): compute / gather / end to end.
 """
 
 from __future__ import annotations
@@ -495,8 +495,9 @@ def config5_probe(world: int, rank: int, dev, peaks: dict) -> dict:
                  rank's buffer over NVLink and then raises a completion flag on every GPU); every GEMV is followed by a wait for
                  all ranks' flags, i.e. the time includes per-GEMM visibility of the full [1, N] on every rank;
                  gather-only = one NCCL all_gather_into_tensor of the same 57 KB, for comparison.
-      M = 4096 : tcgen05 GEMM on the shard + NCCL all_gather_into_tensor of the 235 MB output, software-pipelined (the gather of
-                 GEMM i overlaps GEMM i+1)."""
+      M = 4096 : tcgen05 GEMM on the shard writing straight into a symmetric gather buffer + cb200_push_bulk of the slice from a
+                 high-priority side stream (NVLS multicast stores), software-pipelined: the gather of GEMM i overlaps GEMM i+1
+                 (an NCCL all-gather kernel does not: it runs in the next GEMM's tail, profiles/r02_push_modes_n8_gather.log)."""
     import torch
     import torch.distributed as dist
 
@@ -509,6 +510,7 @@ def config5_probe(world: int, rank: int, dev, peaks: dict) -> dict:
     st = quant_utils.scalar_types.uint4
     shard_bytes = k * n_local // 2
     copies = max(3, min(24, int(2.2 * 126e6 / shard_bytes) + 1))
+    copies += copies & 1  # even: the M=4096 pipeline alternates two gather slots
     layers = [ShardedMixedPrecisionLinear(*quant_utils.random_packed_weights(k, n_local, st, GROUP, torch.float16, dev, seed=900 + 31 * rank + i),
                                           BITS, BIAS, GROUP, already_sharded=True) for i in range(copies)]  # fmt: skip
     hbm = float(peaks.get("hbm_gbs", 6650.0))
@@ -582,20 +584,24 @@ def config5_probe(world: int, rank: int, dev, peaks: dict) -> dict:
                 outs2 = [torch.empty((m, n_local), device=dev, dtype=torch.float16) for _ in range(2)]
                 gbufs = [torch.empty((world * m, n_local), device=dev, dtype=torch.float16) for _ in range(2)]
                 row["gather_us"] = timed(lambda i: dist.all_gather_into_tensor(gbufs[0], outs2[0]), 24, graph=False)
-                pending = [None, None]
+                events = [None, None]
 
                 def piped(i):
                     b = i & 1
-                    if pending[b] is not None:
-                        pending[b].wait()  # buffer b's previous gather is done: its GEMM output may be overwritten
-                    layers[i].local(x, out=outs2[b])
-                    pending[b] = dist.all_gather_into_tensor(gbufs[b], outs2[b], async_op=True)
+                    if events[b] is not None:
+                        torch.cuda.current_stream(dev).wait_event(events[b])  # slot b's previous gather is complete on every rank
+                    # GEMM into this rank's slot of the symmetric [G, M, N/G] buffer, then the slice goes to every peer from a
+                    # high-priority side stream (multimem.st to the NVLS multicast address where there is one) + a device barrier
+                    _, events[b] = layers[i].gathered_push_async(x, slot=b)
 
                 row["e2e_us"] = timed(piped, 48, graph=False)
-                for w in pending:
-                    if w is not None:
-                        w.wait()
-                row["gather"] = "NCCL all_gather_into_tensor, double-buffered: the gather of GEMM i overlaps GEMM i+1"
+                for e in events:
+                    if e is not None:
+                        torch.cuda.current_stream(dev).wait_event(e)
+                torch.cuda.synchronize(dev)
+                row["gather"] = ("cb200_push_bulk on a high-priority side stream (NVLS multicast stores where available, else P2P stores), "
+                                 "double-buffered: the gather of GEMM i overlaps GEMM i+1; gather_us = a stand-alone NCCL all_gather_into_tensor "
+                                 "of the same bytes, for comparison")
             else:
                 row["e2e_us"] = row["compute_us"]
                 row["gather_us"] = 0.0

@@ -264,29 +264,56 @@ def config5(world: int, rank: int, dev, lib) -> dict:
         if w is not None:
             w.wait()
     torch.cuda.synchronize(dev)
-    events = [None, None]
+    try:  # the same on a process group whose NCCL stream has high priority
+        from torch.distributed import ProcessGroupNCCL
 
-    def ce(i):
-        b = i & 1
-        if events[b] is not None:
-            torch.cuda.current_stream(dev).wait_event(events[b])  # slot b's previous gather is complete everywhere
-        _, events[b] = layers[i].gathered_ce_async(xb, slot=b)
+        opts = ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        hp = dist.new_group(backend="nccl", pg_options=opts)
+        pending = [None, None]
 
-    try:
-        out["m4096_ce_piped_us"] = timed(ce, 48, False)
-        for e in events:
-            if e is not None:
-                torch.cuda.current_stream(dev).wait_event(e)
+        def piped_hp(i):
+            b = i & 1
+            if pending[b] is not None:
+                pending[b].wait()
+            layers[i].local(xb, out=outs2[b])
+            pending[b] = dist.all_gather_into_tensor(gbufs[b], outs2[b], group=hp, async_op=True)
+
+        out["m4096_nccl_hiprio_piped_us"] = timed(piped_hp, 48, False)
+        for w in pending:
+            if w is not None:
+                w.wait()
         torch.cuda.synchronize(dev)
-        # values: slot r of the last-used buffer on this rank equals rank r's local result
-        i_last = copies - 1
-        buf = layers[i_last]._symm[(("ce", i_last & 1, m), torch.float16)][0]
-        mine = layers[i_last].local(xb)
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        out["m4096_ce_values_match"] = bool(all(torch.equal(buf[r], gathered[r]) for r in range(world)))
     except Exception as e:  # noqa: BLE001
-        out["m4096_ce_piped_us"] = f"error: {type(e).__name__}: {e}"[:300]
+        out["m4096_nccl_hiprio_piped_us"] = f"error: {type(e).__name__}: {e}"[:300]
+    if rank == 0:
+        print(json.dumps({k_: v_ for k_, v_ in out.items() if k_.startswith("m4096")}), flush=True)
+    for mode, ctas in (("ce", 0), ("p2p", 32), ("p2p", 64), ("multicast", 16), ("multicast", 32)):
+        events = [None, None]
+
+        def bulk(i, mode=mode, ctas=ctas):
+            b = i & 1
+            if events[b] is not None:
+                torch.cuda.current_stream(dev).wait_event(events[b])  # slot b's previous gather is complete everywhere
+            _, events[b] = layers[i].gathered_push_async(xb, slot=b, mode=mode, max_ctas=ctas)
+
+        tag = f"m4096_{mode}{ctas or ''}_piped_us"
+        try:
+            out[tag] = timed(bulk, 48, False)
+            for e in events:
+                if e is not None:
+                    torch.cuda.current_stream(dev).wait_event(e)
+            torch.cuda.synchronize(dev)
+            # values: slot r of the last-used buffer on this rank equals rank r's local result
+            i_last = copies - 1
+            buf = layers[i_last]._symm[(("bulk", i_last & 1, m), torch.float16)][0]
+            mine = layers[i_last].local(xb)
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            out[tag.replace("_piped_us", "_values_match")] = bool(all(torch.equal(buf[r], gathered[r]) for r in range(world)))
+        except Exception as e:  # noqa: BLE001
+            out[tag] = f"error: {type(e).__name__}: {e}"[:300]
+        if rank == 0:
+            print(json.dumps({tag: out[tag]}), flush=True)
     return out
 
 

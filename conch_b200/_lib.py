@@ -37,6 +37,7 @@ EXPORTS = (
     "cb200_wait_flags",
     "cb200_mpgemm_chain",
     "cb200_push",
+    "cb200_push_bulk",
     "cb200_peer_copy",
     "cb200_last_variant",
     "cb200_last_launch_count",
@@ -105,6 +106,8 @@ def load() -> ctypes.CDLL:
         lib.cb200_mpgemm_chain.argtypes = lib.cb200_mpgemm_push_signal.argtypes + [c_void_p, c_int, c_void_p]  # x_flags, count, x_expected
         lib.cb200_push.restype = c_int
         lib.cb200_push.argtypes = [c_void_p, c_size_t, ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p]
+        lib.cb200_push_bulk.restype = c_int
+        lib.cb200_push_bulk.argtypes = [c_void_p, c_size_t, ctypes.POINTER(c_void_p), c_int, c_void_p, c_int, c_void_p]
         lib.cb200_peer_copy.restype = c_int
         lib.cb200_peer_copy.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
         lib.cb200_wait_flags.restype = c_int

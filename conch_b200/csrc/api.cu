@@ -286,12 +286,10 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
     // register-window kernel (bf16 x int8, group sizes that straddle stages); tcgen05 pipeline above.
     const bool decode = M <= 8;
     if (decode || !tc_supported(p, weight_size_bits)) {
-      // (fused gather to 4 or more peers: the register-window kernel, whose column blocks finish -- and push -- at staggered
-      //  times; the streaming kernel's CTAs all store in the same microsecond and the kernel then sits out a full NVLink
-      //  round trip: measured 1.71-3.1 ms against 1.57 ms per 8-GPU step, profiles/r02_bench_n8*.json)
+      // (fused gather: the streaming kernel for any number of peers -- 8 GPUs, 128 pushing GEMVs per token: 1.35 ms against 1.84 ms
+      //  on the register-window kernel and 1.31 ms without any push, profiles/r02_push_modes_n8.log)
       // (the in-kernel wait of cb200_mpgemm_chain exists in the streaming kernel only)
-      chosen = (decode && (num_peers < 4 || p.wait_flags != nullptr) && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM
-                                                                                                                          : CB200_DECODE_MMA;
+      chosen = (decode && stream_supported(p, weight_size_bits, act_dtype)) ? CB200_DECODE_STREAM : CB200_DECODE_MMA;
     } else {
       chosen = CB200_TC_TS;
     }
@@ -306,7 +304,7 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
     return CB200_ERR_UNSUPPORTED;
   }
   if (p.wait_flags != nullptr && chosen != CB200_DECODE_STREAM) {
-    set_error("cb200_mpgemm_chain: only the streaming decode kernel waits for its activations (M <= 16, fp16/bf16 x int4 or fp16 x int8)");
+    set_error("cb200_mpgemm_chain: only the streaming decode kernel waits for its activations (M <= 8, fp16/bf16 x int4 or fp16 x int8)");
     return CB200_ERR_UNSUPPORTED;
   }
   int launches = 0;
@@ -380,6 +378,34 @@ int cb200_push(const void* src, size_t bytes, void* const* peer_dst, int num_pee
     return CB200_ERR_UNSUPPORTED;
   }
   return launch_push(src, bytes, peer_dst, num_peers, peer_flags, local_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cb200_push_bulk(const void* src, size_t bytes, void* const* peer_dst, int num_peers, void* multicast_dst, int max_ctas,
+                    void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!src || !aligned16(src) || bytes == 0 || (bytes & 15u)) {
+    set_error("cb200_push_bulk: src must be 16-byte aligned and bytes a positive multiple of 16 (bytes=%zu)", bytes);
+    return CB200_ERR_ARG;
+  }
+  if (multicast_dst != nullptr) {
+    if (!aligned16(multicast_dst)) {
+      set_error("cb200_push_bulk: multicast_dst is not 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+  } else {
+    if (num_peers < 1 || num_peers > CB200_MAX_PEERS || !peer_dst) {
+      set_error("cb200_push_bulk: num_peers=%d out of range (1..%d) or null pointer array", num_peers, CB200_MAX_PEERS);
+      return CB200_ERR_ARG;
+    }
+    for (int i = 0; i < num_peers; ++i) {
+      if (!peer_dst[i] || !aligned16(peer_dst[i])) {
+        set_error("cb200_push_bulk: peer_dst[%d] null or not 16-byte aligned", i);
+        return CB200_ERR_ARG;
+      }
+    }
+  }
+  return launch_push_bulk(src, bytes, peer_dst, num_peers, multicast_dst, max_ctas, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cb200_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {

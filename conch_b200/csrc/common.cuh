@@ -100,6 +100,8 @@ int launch_scaled(const void* a, const void* b_t, const float* scale_a, const fl
                   int K, int N, int in_kind, int out_dtype, int sa_scalar, int sb_scalar, cudaStream_t stream);
 int launch_static_quant(const void* x, const float* scale, void* out, int64_t n, int in_dtype, int out_kind, cudaStream_t stream);
 int launch_wait_flags(const uint32_t* flags, int count, uint32_t* expected, cudaStream_t stream);
+int launch_push_bulk(const void* src, size_t bytes, void* const* peer_dst, int num_peers, void* multicast_dst, int max_ctas,
+                     cudaStream_t stream);
 int launch_push(const void* src, size_t bytes, void* const* peer_dst, int num_peers, void* const* peer_flags, void* local_flag,
                 cudaStream_t stream);
 struct StreamTuning {

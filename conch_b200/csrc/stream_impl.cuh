@@ -33,7 +33,6 @@ struct StreamGeom {
   int x_bytes;      // staged x slab
   int red_bytes;    // cluster reduction buffers + the group sums of x (at its end)
   int xsum_bytes;
-  int x_rot;        // staging of x: per-CTA rotation of the warps' 512-byte tasks (0 = none)
   int win_stages;   // 16-row variant: stages of x staged at a time (the slab of x is windowed so that the weight ring keeps its depth)
   int no_hint;      // debug (cb200_set_stream_tuning ring_kb < 0): weight tiles without the L2 evict_first policy
   unsigned int* done;  // cb200_mpgemm_push_signal: self-resetting counter of finished 32-column slices (workspace), else unused
@@ -224,7 +223,8 @@ __device__ __forceinline__ void quad_math(Accum<MT, BITS == 4>& a, const uint4 w
 }  // namespace ring
 
 // A: activation type, BITS: 4 | 8, MT: 8-row tiles of x (1: M <= 8, 2: M <= 16).
-template <class A, int BITS, int MT>
+// CHAIN: cb200_mpgemm_chain -- the consumers wait for the completion counters of x inside the kernel (M <= 8 instantiations only).
+template <class A, int BITS, int MT, bool CHAIN>
 __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15, 1)
     stream_kernel(const __grid_constant__ CUtensorMap tmw, const Problem p, const StreamGeom geo) {
   using namespace ring;
@@ -330,8 +330,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
   constexpr int XR = 8 * MT;                           // rows of the sums table
   const uint32_t xsum = recv + geo.red_bytes - geo.xsum_bytes;  // [stage][scale row][XR] fp32: sums of x over the quads of a scale row
   asm volatile("griddepcontrol.wait;" ::: "memory");  // x, out and the peers belong to the stream order
-  const bool chained = p.wait_flags != nullptr;
-  if (chained) {
+  if constexpr (CHAIN) {
     // cb200_mpgemm_chain: x is a gather buffer the other GPUs push into.  One warp spins until every rank's completion counter
     // has reached this call's number (system-scope acquire), the rest of the consumers wait at the barrier; the producer warp is
     // not involved -- the ring keeps filling with weights meanwhile.
@@ -367,32 +366,27 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
     const int esh = (BITS == 4 ? 2 : 1) + mshift;  // chunks per scale row = 1 << esh
     const int e0 = wi0 * geo.gps;                  // first entry of the sums table in the window
     const char* xg = reinterpret_cast<const char*>(p.x) + size_t(qa0) * F::XQ;
-    constexpr int XU = MT == 1 ? 4 : 8;  // loads in flight per thread
-    // Every CTA reads the same rows of x at the same moment -- a broadcast the L2 serves line by line.  The warps' 512-byte tasks are
-    // therefore rotated by a per-CTA offset (geo.x_rot tasks per CTA), so that at any instant the CTAs ask for different lines.
-    const int ntask = (M * cpr + 31) >> 5, nwc = nthr >> 5;
-    const int rot = geo.x_rot ? int((unsigned(blockIdx.y * gridDim.x + blockIdx.x) * unsigned(geo.x_rot)) % unsigned(ntask)) : 0;
-    for (int task0 = warp; task0 < ntask; task0 += XU * nwc) {
+    constexpr int XU = 4;  // loads in flight per thread
+    for (int base0 = threadIdx.x & ~31; base0 < M * cpr; base0 += XU * nthr) {
       uint4 v[XU];
       int mm[XU], cv[XU];
       bool ok[XU];
 #pragma unroll
       for (int u = 0; u < XU; ++u) {
-        int tr = task0 + u * nwc + rot;
-        if (tr >= ntask) tr -= ntask;
-        const int idx = tr * 32 + lane;
+        const int idx = base0 + u * nthr + lane;
         mm[u] = idx / cpr;
         cv[u] = cw0 + idx - mm[u] * cpr;
         ok[u] = idx < M * cpr && cv[u] >= c_lo && cv[u] < c_hi;
         v[u] = make_uint4(0u, 0u, 0u, 0u);
         if (ok[u]) {  // (a pushed-into x is read past L1: these lines were written by other GPUs while this kernel was resident)
           const uint4* src = reinterpret_cast<const uint4*>(xg + size_t(mm[u]) * p.K * 2) + cv[u];
-          v[u] = chained ? __ldcg(src) : __ldg(src);
+          if constexpr (CHAIN) v[u] = __ldcg(src);
+          else v[u] = __ldg(src);
         }
       }
 #pragma unroll
       for (int u = 0; u < XU; ++u) {
-        if (task0 + u * nwc >= ntask) break;  // (warp-uniform)
+        if (base0 + u * nthr >= M * cpr) break;  // (warp-uniform)
         float sum = 0.f;
         if (ok[u]) {
           uint4 o = v[u];
@@ -584,9 +578,9 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
 
   const int i_full0 = q_lo > qa0 ? 1 : 0, i_full1 = (q_hi - qa0) >> 2;  // stages [i_full0, i_full1) lie wholly inside the slab
   int i = grp;
-  const int wst = MT == 1 ? nstages : geo.win_stages;  // (M <= 8: one window)
-  for (int wi0 = 0; wi0 < nstages; wi0 += wst) {
-  const int wi1 = min(nstages, wi0 + wst);
+  // (M <= 8: exactly one window -- written so that the compiler sees a single trip)
+  for (int wi0 = 0; wi0 < (MT == 1 ? 1 : nstages); wi0 += (MT == 1 ? 1 : geo.win_stages)) {
+  const int wi1 = MT == 1 ? nstages : min(nstages, wi0 + geo.win_stages);
   if (MT > 1 && wi0 > 0) asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");  // every warp is done with the previous window of x
   stage_x(wi0, wi1);
   enter_window(wi0);
@@ -723,10 +717,10 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-template <class A, int BITS, int MT>
+template <class A, int BITS, int MT, bool CHAIN>
 static int launch_stream_mt(const CUtensorMap& mw, const Problem& p, const StreamGeom& geo, dim3 grid, size_t smem, bool pdl,
                             cudaStream_t stream) {
-  auto kern = stream_kernel<A, BITS, MT>;
+  auto kern = stream_kernel<A, BITS, MT, CHAIN>;
   static unsigned long long attr_mask = 0;  // per (instantiation, device)
   {
     const DeviceInfo* di = current_device_info();
@@ -764,8 +758,9 @@ static int launch_stream_mt(const CUtensorMap& mw, const Problem& p, const Strea
 template <class A, int BITS>
 static int launch_stream_typed(const CUtensorMap& mw, const Problem& p, const StreamGeom& geo, dim3 grid, size_t smem, bool pdl,
                                cudaStream_t stream) {
-  return geo.m_rows > 8 ? launch_stream_mt<A, BITS, 2>(mw, p, geo, grid, smem, pdl, stream)
-                        : launch_stream_mt<A, BITS, 1>(mw, p, geo, grid, smem, pdl, stream);
+  if (p.wait_flags != nullptr) return launch_stream_mt<A, BITS, 1, true>(mw, p, geo, grid, smem, pdl, stream);  // (M <= 8: launch_stream)
+  return geo.m_rows > 8 ? launch_stream_mt<A, BITS, 2, false>(mw, p, geo, grid, smem, pdl, stream)
+                        : launch_stream_mt<A, BITS, 1, false>(mw, p, geo, grid, smem, pdl, stream);
 }
 
 // one entry per translation unit

@@ -29,8 +29,6 @@
 #include <atomic>
 
 #include "host_util.cuh"
-#include <cstdlib>
-
 #include "stream_impl.cuh"
 
 namespace cb200 {
@@ -177,8 +175,8 @@ int launch_stream(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     set_error("cb200_mpgemm_push_signal / cb200_mpgemm_chain need the %d-byte counter area of the workspace", CB200_WORKSPACE_COUNTER_BYTES);
     return CB200_ERR_WORKSPACE;
   }
-  if (p_in.wait_flags != nullptr && p_in.M > 16) {
-    set_error("cb200_mpgemm_chain: one pass of the decode kernel (M <= 16)");
+  if (p_in.wait_flags != nullptr && p_in.M > 8) {
+    set_error("cb200_mpgemm_chain: one 8-row pass of the streaming decode kernel (M <= 8)");
     return CB200_ERR_UNSUPPORTED;
   }
   if (size_t(p_in.K / p_in.g) * p_in.N >= (size_t(1) << 31)) {
@@ -220,13 +218,6 @@ int launch_stream(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
     geo.red_bytes = pl.red_bytes;
     geo.xsum_bytes = pl.xsum_bytes;
     geo.win_stages = pl.win_stages;
-    {
-      static const int x_rot_env = [] {
-        const char* e = getenv("CB200_STREAM_XROT");  // A/B knob of the x-staging rotation (tasks per CTA; default below)
-        return e ? atoi(e) : -1;
-      }();
-      geo.x_rot = x_rot_env >= 0 ? x_rot_env : 0;
-    }
     geo.done = ws ? reinterpret_cast<unsigned int*>(ws) + (CB200_WORKSPACE_COUNTER_BYTES / 4 - 1) : nullptr;
     geo.no_hint = g_stream_tuning.dbg & 1;
     geo.trace = g_stream_trace;

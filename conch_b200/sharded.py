@@ -127,6 +127,7 @@ class ShardedMixedPrecisionLinear:
     # ---- side streams (per device, shared by all layers): the decoupled push and the copy-engine gather run there --------
     _side: dict[int, "torch.cuda.Stream"] = {}
     _peer_streams: dict[int, list["torch.cuda.Stream"]] = {}
+    _hi_prio: dict[int, "torch.cuda.Stream"] = {}
 
     @classmethod
     def _side_stream(cls, device: torch.device) -> "torch.cuda.Stream":
@@ -175,40 +176,66 @@ class ShardedMixedPrecisionLinear:
         if idx in cls._side:
             torch.cuda.current_stream(device).wait_stream(cls._side[idx])
 
-    def gathered_ce_async(self, x: torch.Tensor, slot: int = 0, **kwargs) -> tuple[torch.Tensor, "torch.cuda.Event | None"]:
-        """Large-M all-gather on the COPY ENGINES: the GEMM writes this rank's `[M, N/G]` slice straight into its slot of a
-        symmetric `[G, M, N/G]` buffer, then one `cudaMemcpyAsync` per peer (each on its own side stream, so the copies run on
-        different engines at once) stores the slice into the same slot of that peer's buffer, and a device-side barrier across
-        the ranks closes the gather.  No SM is involved, so -- unlike an NCCL kernel, which cannot become resident while the next
-        GEMM's one-CTA-per-SM grid holds the shared memory -- the transfer really overlaps the next GEMM.  Returns the buffer
-        (two of them alternate: `slot` 0 / 1) and an event; `current_stream().wait_event(event)` before reading the peers'
-        slots, and before the call after next on the same slot may overwrite the local one."""
-        y_shape = (x.shape[0], self.n_local)
+    def gathered_push_async(self, x: torch.Tensor, slot: int = 0, *, mode: str = "auto", max_ctas: int = 0,
+                            **kwargs) -> tuple[torch.Tensor, "torch.cuda.Event | None"]:
+        """Large-M all-gather that OVERLAPS the next GEMM: the GEMM writes this rank's `[M, N/G]` slice straight into its slot
+        of a symmetric `[G, M, N/G]` buffer; the slice then travels to the same slot of every peer's buffer from a side stream,
+        and a device-side barrier across the ranks closes the gather.  An NCCL all-gather kernel does not overlap here: it is
+        enqueued behind the next GEMM's CTAs and runs in that GEMM's tail (measured: end to end = GEMM + gather).  `mode`:
+          "multicast"  `cb200_push_bulk` on a HIGH-PRIORITY stream, one `multimem.st` per 16 bytes to the NVLS multicast address
+                       of the buffer (the switch replicates: the sender's egress is the slice once) -- "auto" when the symmetric-
+                       memory handle has a multicast pointer;
+          "p2p"        the same kernel with one plain store per peer -- "auto" otherwise;
+          "ce"         one `cudaMemcpyAsync` per peer on per-peer streams (copy engines, no SM at all).
+        `max_ctas` bounds the SMs the push takes from the next GEMM (0: 16 for multicast, 32 for p2p).  Returns the buffer (two
+        alternate: `slot` 0 / 1) and an event; `current_stream().wait_event(event)` before reading the peers' slots, and before
+        the call after next on the same slot may overwrite the local one."""
+        m = x.shape[0]
         out_dtype = kwargs.get("output_dtype") or x.dtype
         if self.world == 1:
             return self.local(x, **kwargs).unsqueeze(0), None
-        key = (("ce", slot, y_shape[0]), out_dtype)
-        buf, hdl, peers = self._symmetric(y_shape[0], out_dtype, x.device, key=key)
+        key = (("bulk", slot, m), out_dtype)
+        buf, hdl, peers = self._symmetric(m, out_dtype, x.device, key=key)
         self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size, out=buf[self.rank], **kwargs)
+        import ctypes
+
         from conch_b200 import _lib
 
         lib = _lib.load()
         idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
-        streams = self._peer_streams.setdefault(idx, [])
-        while len(streams) < len(peers):
-            streams.append(torch.cuda.Stream(device=x.device))
         cur = torch.cuda.current_stream(x.device)
-        side = self._side_stream(x.device)
-        nbytes = y_shape[0] * self.n_local * buf.element_size()
+        if idx not in self._hi_prio:
+            self._hi_prio[idx] = torch.cuda.Stream(device=x.device, priority=-1)
+        side = self._hi_prio[idx]
+        nbytes = m * self.n_local * buf.element_size()
         src = buf[self.rank].data_ptr()
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mode == "auto":
+            mode = "multicast" if mc else "p2p"
         with torch.cuda.device(x.device):
-            for st, dst in zip(streams, peers):
-                st.wait_stream(cur)
-                _lib.raise_for_status(lib.cb200_peer_copy(dst, src, nbytes, st.cuda_stream))
-            for st in streams[: len(peers)]:
-                side.wait_stream(st)
+            if mode == "ce":
+                streams = self._peer_streams.setdefault(idx, [])
+                while len(streams) < len(peers):
+                    streams.append(torch.cuda.Stream(device=x.device))
+                for st, dst in zip(streams, peers):
+                    st.wait_stream(cur)
+                    _lib.raise_for_status(lib.cb200_peer_copy(dst, src, nbytes, st.cuda_stream))
+                for st in streams[: len(peers)]:
+                    side.wait_stream(st)
+            else:
+                side.wait_stream(cur)
+                peer_arr = (ctypes.c_void_p * len(peers))(*peers)
+                if mode == "multicast":
+                    if not mc:
+                        raise RuntimeError("this symmetric-memory allocation has no multicast address (NVLS unavailable)")
+                    mc_dst = mc + self.rank * nbytes
+                    _lib.raise_for_status(lib.cb200_push_bulk(src, nbytes, peer_arr, len(peers), mc_dst, max_ctas or 16, side.cuda_stream))
+                elif mode == "p2p":
+                    _lib.raise_for_status(lib.cb200_push_bulk(src, nbytes, peer_arr, len(peers), None, max_ctas or 32, side.cuda_stream))
+                else:
+                    raise ValueError(f"unknown gather mode {mode!r}")
             with torch.cuda.stream(side):
-                hdl.barrier(channel=2 + slot)  # every rank's copies have landed everywhere
+                hdl.barrier(channel=2 + slot)  # every rank's slice has landed everywhere
                 done = torch.cuda.Event()
                 done.record(side)
         return buf, done

@@ -151,7 +151,7 @@ CB200_API int cb200_wait_flags(const void* flags, int count, void* expected, voi
  * *x_expected + 1.  The WAIT HAPPENS INSIDE THE KERNEL: its consumer warps spin on the counters while the producer warp already
  * fills the shared-memory ring with this GEMV's weights, so the NVLink latency of the previous GEMV's push overlaps this one's
  * prologue -- no wait kernel, no barrier, no NCCL.  The grid's last block advances *x_expected (device memory, zero-initialised),
- * so one chained call per signalled producer is safe under CUDA-graph replay.  Streaming decode kernel only (M <= 16; AUTO
+ * so one chained call per signalled producer is safe under CUDA-graph replay.  Streaming decode kernel only (M <= 8; AUTO
  * selects it).  peer_out / peer_flags / local_flag as in cb200_mpgemm_push_signal (num_peers == 0 and local_flag == NULL: the
  * result stays local).  x_flags == NULL: plain cb200_mpgemm_push_signal. */
 CB200_API int cb200_mpgemm_chain(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
@@ -170,6 +170,15 @@ CB200_API int cb200_mpgemm_chain(const void* x, const void* w_q_packed, const vo
  * not released, before its remote stores are acknowledged).  A signalled push is one CTA (<= 1 MiB). */
 CB200_API int cb200_push(const void* src, size_t bytes, void* const* peer_dst, int num_peers,
                  void* const* peer_flags, void* local_flag, void* stream);
+
+/* The large-M leg of the gather: the same copy by up to `max_ctas` CTAs (0 = as many as the bytes are worth, one per SM at most),
+ * no completion counters -- close it with a cross-GPU barrier.  multicast_dst != NULL: one `multimem.st` per 16 bytes to an NVLS
+ * multicast address that maps this rank's slot of EVERY GPU's buffer (torch symmetric memory: handle.multicast_ptr + slot
+ * offset) -- the switch replicates, the sender's egress is the slice once; peer_dst is then ignored.  Meant for a HIGH-PRIORITY
+ * side stream next to the following GEMM: the GEMM's CTAs carry 60 K registers, so the push needs SMs of its own and gets them
+ * as GEMM CTAs retire (conch_b200/sharded.py gathered_push_async). */
+CB200_API int cb200_push_bulk(const void* src, size_t bytes, void* const* peer_dst, int num_peers, void* multicast_dst,
+                 int max_ctas, void* stream);
 
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): the copy-engine leg of the large-M all-gather -- every rank
  * copies its [M, N/G] slice into its slot of every peer's buffer from per-peer side streams while the next GEMM owns the SMs

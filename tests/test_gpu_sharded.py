@@ -60,6 +60,41 @@ def _worker(rank: int, world: int, port: int, ret) -> None:
                     layer.sync()  # (the test re-uses the buffer right away: nobody may still be reading it)
                     torch.cuda.synchronize()
                     assert torch.equal(got, mixed_precision_gemm(sign * x, wq, ws, wzp, 4, 0, 128)), f"pushed_signalled != single at M={m}"
+                # decoupled push: the GEMV stores locally, cb200_push on a side stream carries the slice and raises the counters
+                for sign in (1.0, -1.0):
+                    buf = layer.pushed_async(sign * x)
+                    layer.wait()
+                    got = buf.permute(1, 0, 2).reshape(m, -1).clone()
+                    ShardedMixedPrecisionLinear.join(x.device)
+                    layer.sync()
+                    torch.cuda.synchronize()
+                    assert torch.equal(got, mixed_precision_gemm(sign * x, wq, ws, wzp, 4, 0, 128)), f"pushed_async != single at M={m}"
+                # chain: the SECOND layer's kernel itself waits for the first layer's counters (cb200_mpgemm_chain): its activations
+                # are the first layer's gathered output
+                layer2 = ShardedMixedPrecisionLinear(wq[: 512 // 8], ws[: 512 // 128], wzp[: 512 // 128], 4, 0, 128)  # K = 512 = layer's N
+                for sign in (1.0, -1.0):
+                    buf = layer.pushed_signalled(sign * x)
+                    hx = buf.view(1, -1) if m == 1 else None
+                    if hx is not None:  # (M = 1: [G, 1, N/G] IS [1, N] in memory -- the gather buffer is the next layer's x)
+                        buf2 = layer2.pushed_signalled(hx, after=layer)
+                        layer2.wait()
+                        got2 = buf2.permute(1, 0, 2).reshape(m, -1).clone()
+                        layer.sync()
+                        torch.cuda.synchronize()
+                        want1 = mixed_precision_gemm(sign * x, wq, ws, wzp, 4, 0, 128)
+                        want2 = mixed_precision_gemm(want1, wq[: 512 // 8].contiguous(), ws[: 512 // 128].contiguous(), wzp[: 512 // 128].contiguous(), 4, 0, 128)
+                        assert torch.equal(got2, want2), f"chained != single at M={m}"
+                    else:
+                        layer.wait()
+                        layer.sync()
+                        torch.cuda.synchronize()
+            else:
+                # large M: the slice travels from a high-priority side stream (multicast stores / P2P stores / copy engines)
+                for mode in ("auto", "p2p", "ce"):
+                    buf, ev = layer.gathered_push_async(x, slot=0, mode=mode)
+                    torch.cuda.current_stream().wait_event(ev)
+                    torch.cuda.synchronize()
+                    assert torch.equal(buf.permute(1, 0, 2).reshape(m, -1), single), f"gathered_push_async({mode}) != single at M={m}"
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
