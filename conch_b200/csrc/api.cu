@@ -284,7 +284,9 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
     // regime split by MEASUREMENT (profiles/r02_*): HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x) on the
     // streaming ring kernel where it has an operand format and a stage layout for the problem, else on round 1's
     // register-window kernel (bf16 x int8, group sizes that straddle stages); tcgen05 pipeline above.
-    const bool decode = M <= 8;
+    // (M = 9..16: the streaming kernel's 16-row variant where it has a format for the problem -- 3 to 17 % ahead of the tcgen05
+    //  kernel on the four Llama-3-8B shapes, profiles/r02_decode_table_m16.log; otherwise tcgen05, as for everything above)
+    const bool decode = M <= 8 || (M <= 16 && stream_supported(p, weight_size_bits, act_dtype));
     if (decode || !tc_supported(p, weight_size_bits)) {
       // (fused gather: the streaming kernel for any number of peers -- 8 GPUs, 128 pushing GEMVs per token: 1.35 ms against 1.84 ms
       //  on the register-window kernel and 1.31 ms without any push, profiles/r02_push_modes_n8.log)

@@ -151,6 +151,7 @@ template <int MT, bool HAS_Q>
 struct Accum {
   float P[MT][2][4];
   float Q[HAS_Q ? MT : 1][2][4];
+  float XS[MT][4];  // 16-row variant only: sums of x over the open scale group, by an MMA against an all-ones operand
 };
 
 // One quad: this lane's 4 packed words (4 columns, packed row 4 * quad + t) against its activations.
@@ -160,6 +161,18 @@ template <class A, int BITS, int MT, bool FRESH>
 __device__ __forceinline__ void quad_math(Accum<MT, BITS == 4>& a, const uint4 wv, const uint4 (&xv)[MT]) {
   using F = Fmt<A, BITS>;
   const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+  if constexpr (MT > 1) {
+    // X[m] = sum_k x[m, k] for the zero-point term: the 16-row variant has no staging pass that could sum x on the side (its x
+    // arrives by bulk copy and is used as it lies), so an all-ones 16-row operand makes every row of D the column sums of x^T --
+    // c0 / c1 are X[2t], X[2t + 1], the layout the accumulators want.  Exact: products by 1.0, fp32 accumulation.
+    constexpr uint32_t kOnes = F::HALF ? 0x3c003c00u : 0x3f803f80u;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      if constexpr (FRESH) mma_zero<A>(a.XS[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].x, xv[mt].y);
+      else mma_acc<A>(a.XS[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].x, xv[mt].y);
+      if constexpr (BITS == 4) mma_acc<A>(a.XS[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].z, xv[mt].w);
+    }
+  }
   if constexpr (BITS == 4) {
     uint32_t d[4][4];
 #pragma unroll
@@ -239,6 +252,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
   const int rank = blockIdx.x, cb = blockIdx.y;  // gridDim.x == S == cluster size: blockIdx.x is the rank in the cluster
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t bar_full = sbase, bar_empty = sbase + 8 * kStreamMaxRing, bar_red = sbase + 16 * kStreamMaxRing;
+  const uint32_t bar_x = sbase + 512;
   const uint32_t xs = sbase + kStreamHdr;
   const uint32_t recv = xs + geo.x_bytes;
   const uint32_t stages = (recv + geo.red_bytes + 1023u) & ~1023u;
@@ -251,6 +265,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
       mbar_init(bar_full + 8 * lane, 1);
       mbar_init(bar_empty + 8 * lane, nw);
     }
+    if (MT > 1 && lane == 0) mbar_init(bar_x, 1);  // 16-row variant: the windows of x arrive by bulk copy
     if (S > 1 && rank + lane * S < nw) {  // the column slices (one per warp of a consumer group) this CTA reduces
       mbar_init(bar_red + 8 * lane, 1);
       mbar_expect_tx(bar_red + 8 * lane, uint32_t(S * NGRP) * uint32_t(M) * 128u);
@@ -358,6 +373,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
   // per (stage, scale row): consecutive lanes hold the chunks of one stage of one row -> a fixed shuffle tree, the same whatever M
   // is.  M <= 8: one window = the whole slab.  16 rows: windows of geo.win_stages stages -- a whole slab of 16 rows (128 KB at
   // K = 4096) would leave the weight ring four stages, too few bytes in flight to cover the HBM latency.
+  uint32_t x_phase = 0;
   auto stage_x = [&](int wi0, int wi1) {
     constexpr int CPS = 4 * F::CPQ;              // chunks per stage and row
     const int cw0 = wi0 * CPS;                   // first chunk of the window, counted from the aligned start qa0
@@ -366,6 +382,23 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
     const int esh = (BITS == 4 ? 2 : 1) + mshift;  // chunks per scale row = 1 << esh
     const int e0 = wi0 * geo.gps;                  // first entry of the sums table in the window
     const char* xg = reinterpret_cast<const char*>(p.x) + size_t(qa0) * F::XQ;
+    if constexpr (MT > 1) {
+      // 16 rows: one bulk copy per row brings the window in, and that is all -- the register-staged pass below (a round trip per
+      // four chunks and thread, a shuffle tree per chunk) cost 11 us of a 38 us kernel at 16 rows (profiles/r02_stream_m16_ncu.txt).
+      const int c_end = min(c_hi, cw0 + cpr);
+      const uint32_t row_bytes = uint32_t(c_end - c_lo) * 16u;
+      if (warp == 0) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous window was read / written by ordinary accesses
+          mbar_expect_tx(bar_x, uint32_t(M) * row_bytes);
+        }
+        __syncwarp();
+        if (lane < M) bulk_g2s(xs + lane * geo.x_pitch, xg + size_t(lane) * p.K * 2 + size_t(c_lo) * 16, row_bytes, bar_x);
+      }
+      mbar_wait(bar_x, x_phase);
+      x_phase ^= 1u;
+      return;  // used as it lies: the consumers permute their chunks in registers and sum x with an MMA (quad_math)
+    }
     constexpr int XU = 4;  // loads in flight per thread
     for (int base0 = threadIdx.x & ~31; base0 < M * cpr; base0 += XU * nthr) {
       uint4 v[XU];
@@ -378,7 +411,8 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
         cv[u] = cw0 + idx - mm[u] * cpr;
         ok[u] = idx < M * cpr && cv[u] >= c_lo && cv[u] < c_hi;
         v[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok[u]) {  // (a pushed-into x is read past L1: these lines were written by other GPUs while this kernel was resident)
+        if (ok[u]) {
+          // (a pushed-into x is read past L1: these lines were written by other GPUs while this kernel was resident)
           const uint4* src = reinterpret_cast<const uint4*>(xg + size_t(mm[u]) * p.K * 2) + cv[u];
           if constexpr (CHAIN) v[u] = __ldcg(src);
           else v[u] = __ldg(src);
@@ -495,7 +529,8 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
           const int c = 2 * tl + (i >> 1);
           float G = qa.P[mt][tl][i];
           if constexpr (HAS_Q) G = fmaf(qa.Q[mt][tl][i], F::QSCALE, G);
-          acc[mt][tl][i] = fmaf(sa[c], G, fmaf(sb[c], X[mt][i & 1], acc[mt][tl][i]));
+          const float xsum_m = MT > 1 ? qa.XS[mt][i & 1] : X[mt][i & 1];
+          acc[mt][tl][i] = fmaf(sa[c], G, fmaf(sb[c], xsum_m, acc[mt][tl][i]));
         }
   };
   auto clear_pq = [&]() {
@@ -506,9 +541,11 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
         qa.P[mt][0][k] = qa.P[mt][1][k] = 0.f;
         if constexpr (HAS_Q) qa.Q[mt][0][k] = qa.Q[mt][1][k] = 0.f;
         X[mt][k & 1] = 0.f;
+        if constexpr (MT > 1) qa.XS[mt][k] = 0.f;
       }
   };
   auto add_xsum = [&](int entry) {
+    if constexpr (MT > 1) return;  // (summed by quad_math)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const uint2 xr = lds64(lane_xs + entry * (XR * 4) + mt * 32);
@@ -521,7 +558,15 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       if constexpr (BITS == 4) {
-        xv[mt] = lds128(lane_x[mt] + quad * F::XQ);
+        const uint4 v = lds128(lane_x[mt] + quad * F::XQ);
+        if constexpr (MT > 1) {  // raw chunk -> operand order {(k0,k4), (k2,k6), (k1,k5), (k3,k7)}
+          xv[mt].x = prmt(v.x, v.z, 0x5410u);
+          xv[mt].y = prmt(v.y, v.w, 0x5410u);
+          xv[mt].z = prmt(v.x, v.z, 0x7632u);
+          xv[mt].w = prmt(v.y, v.w, 0x7632u);
+        } else {
+          xv[mt] = v;
+        }
       } else {
         const uint2 v = lds64(lane_x[mt] + quad * F::XQ);
         xv[mt] = make_uint4(v.x, v.y, 0u, 0u);
@@ -609,11 +654,10 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
             load_x(xv[j], qa0 + 4 * i + j);
           }
           set_scales(st, 0);
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint2 xr = lds64(lane_xs + i * (XR * 4) + mt * 32);
-            X[mt][0] = __uint_as_float(xr.x);
-            X[mt][1] = __uint_as_float(xr.y);
+          if constexpr (MT == 1) {
+            const uint2 xr = lds64(lane_xs + i * (XR * 4));
+            X[0][0] = __uint_as_float(xr.x);
+            X[0][1] = __uint_as_float(xr.y);
           }
           quad_math<A, BITS, MT, true>(qa, wv[0], xv[0]);
 #pragma unroll

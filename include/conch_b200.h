@@ -62,7 +62,7 @@ enum cb200_variant {
   CB200_TC_SS = 2,        /* tcgen05: TMA -> smem dequant (K-major, 128B swizzle) -> UMMA (both operands smem), TMEM accumulators */
   CB200_TC_TS = 3,        /* tcgen05: TMA -> dequant straight into TMEM (W is the TMEM A operand), x tile from smem */
   CB200_TC2_TS = 4,       /* persistent tcgen05 kernel: m_tile 128, two TMEM accumulators, epilogue overlaps the next tile */
-  CB200_DECODE_STREAM = 5 /* <= 16 rows per pass (AUTO: M <= 8): warp-specialised streaming GEMV -- a producer warp keeps a ring of TMA weight
+  CB200_DECODE_STREAM = 5 /* <= 16 rows per pass (AUTO: M <= 16 where it has an operand format for the problem): warp-specialised streaming GEMV -- a producer warp keeps a ring of TMA weight
                              tiles in shared memory full (it never waits for the stream order: under programmatic dependent launch
                              the ring fills while the previous kernel drains), 12-16 consumer warps turn nibbles into subnormal fp16
                              MMA operands, K is split over a thread-block cluster whose partial sums meet in distributed shared
@@ -116,7 +116,7 @@ CB200_API int cb200_mpgemm_bias(const void* x, const void* w_q_packed, const voi
  * process, to an [M, N] buffer of another GPU (CUDA IPC / symmetric memory): typically this rank's slot of every other
  * rank's gather buffer, so an N-sharded layer needs no separate all-gather.  The stores are plain P2P writes over NVLink,
  * visible to the peer once this kernel has completed; synchronising the ranks (one barrier per token, say) is the
- * caller's job.  Decode kernels only: AUTO picks one for M <= 8, variant = CB200_DECODE_MMA / CB200_DECODE_STREAM forces
+ * caller's job.  Decode kernels only: AUTO picks one for M <= 8 (M <= 16 where the streaming kernel supports the problem), variant = CB200_DECODE_MMA / CB200_DECODE_STREAM forces
  * it for any M (16 rows per pass); any other choice returns CB200_ERR_UNSUPPORTED -- large outputs are bandwidth-bound and
  * belong to an all-gather. */
 CB200_API int cb200_mpgemm_push(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
@@ -132,7 +132,7 @@ CB200_API int cb200_mpgemm_push(const void* x, const void* w_q_packed, const voi
  * zero-initialised).  A consumer on any GPU that needs the gathered output waits until all `world` counters of ITS array have
  * reached the number of signalled GEMVs so far: cb200_wait_flags keeps that number in `*expected` (device memory, zero-
  * initialised, advanced by the wait itself), so a signalled GEMV followed by ONE wait on every rank is safe to capture in a
- * CUDA graph and replay.  Decode kernels only (AUTO: M <= 8; M <= 16 with variant = CB200_DECODE_MMA / CB200_DECODE_STREAM).
+ * CUDA graph and replay.  Decode kernels only (AUTO: M <= 8, or <= 16 where the streaming kernel supports the problem; M <= 16 with variant = CB200_DECODE_MMA / CB200_DECODE_STREAM).
  * local_flag == NULL: plain cb200_mpgemm_push. */
 CB200_API int cb200_mpgemm_push_signal(const void* x, const void* w_q_packed, const void* w_s, const void* w_zp, void* out,
                  int64_t M, int64_t K, int64_t N,

@@ -369,7 +369,7 @@ def test_full_size_row_selection_and_dequant(k, n):
 
 
 def test_batch_rows_equal_single_rows():
-    """Row m of an M=16 call against the M=1 call on that row.  AUTO sends M=16 to the tcgen05 kernel, which rounds W to fp16
+    """Row m of an M=24 call against the M=1 call on that row.  AUTO sends M=24 to the tcgen05 kernel, which rounds W to fp16
     exactly like the reference, and M=1 to the streaming kernel, which keeps s*(q-zp) unrounded in fp32: the two differ by
     sum_k x_k * delta_k with delta_k the fp16 rounding error of W[k,n], |delta_k| <= 2^-11 |W| (half an ulp), independent and
     close to uniform, so rms(delta) <= 2^-10 max|W| / sqrt(12).  The tolerance is 6 sigma of that sum -- derived, not picked
@@ -379,7 +379,7 @@ def test_batch_rows_equal_single_rows():
     k, n = 4096, 6144
     wq, ws, wzp = quant_utils.random_packed_weights(k, n, quant_utils.scalar_types.uint4, 128, torch.float16, "cuda", seed=2)
     gen = torch.Generator(device="cuda").manual_seed(1)
-    x = torch.randn((16, k), generator=gen, device="cuda", dtype=torch.float16)
+    x = torch.randn((24, k), generator=gen, device="cuda", dtype=torch.float16)
     w = dequantize_weights(wq, ws, wzp, 4, 0, 128)
     sigma = math.sqrt(k) * float(x.float().pow(2).mean().sqrt()) * (2.0**-10 * float(w.abs().max())) / math.sqrt(12.0)
     full = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32)

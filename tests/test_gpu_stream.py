@@ -66,7 +66,10 @@ def test_auto_dispatch_and_unsupported_formats():
 
     assert auto(1, 512, 256, "uint4", 128, torch.float16) == STREAM
     assert auto(8, 512, 256, "uint4", 128, torch.float16) == STREAM
-    assert auto(9, 512, 256, "uint4", 128, torch.float16) == _lib.TC_TS
+    assert auto(9, 512, 256, "uint4", 128, torch.float16) == STREAM  # 16-row variant
+    assert auto(16, 512, 256, "uint4", 128, torch.float16) == STREAM
+    assert auto(17, 512, 256, "uint4", 128, torch.float16) == _lib.TC_TS
+    assert auto(12, 512, 256, "uint8", 128, torch.bfloat16) == _lib.TC_TS  # no streaming format: tcgen05 above 8 rows
     assert auto(4, 512, 256, "uint8", 128, torch.float16) == STREAM
     assert auto(4, 512, 256, "uint4b8", -1, torch.bfloat16) == STREAM
     assert auto(4, 512, 256, "uint8", 128, torch.bfloat16) == _lib.DECODE_MMA  # 128 + q does not fit a bf16 significand
