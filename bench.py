@@ -323,10 +323,16 @@ def run_gpu_arm(args) -> None:
         barrier()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream ------------------------------------
+    sampler = ClockSampler(local_rank)  # (NVML initialised BEFORE the barrier: tens of milliseconds, different on every rank)
     with torch.cuda.stream(stream):
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        with ClockSampler(local_rank) as clocks:
+        if world > 1 and not args.nccl_gather and use_graph:
+            # device-side cross-GPU barrier in front of the start event: the ranks' HOST threads leave the barrier above up to
+            # milliseconds apart, and a rank that enqueues early would count its wait for the last one at the first token's
+            # barrier as step time (20 steps: +8 % at 8 GPUs).  The timed region starts when every GPU is there.
+            sharded[0][0].sync()
+        with sampler as clocks:
             start.record(stream)
             for _ in range(args.steps):
                 if graph is not None:
@@ -384,15 +390,21 @@ def run_gpu_arm(args) -> None:
     e2e_steps = max(3, min(args.steps, 50))
     for _ in range(3):
         e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # wall clock through Python, max over ranks; best of three passes of e2e_steps steps -- the host side shares 16 cores with the
+    # other ranks' launch, NCCL and NVML threads, and a single 40 ms stall in one rank doubles a 20-step average
+    e2e_passes = 3
+    t = None
+    for _ in range(e2e_passes):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        tp = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        t = tp if t is None or float(tp.item()) < float(t.item()) else t
     e2e_value = bytes_step / float(t.item()) / 1e9
     h2d = sum(x.numel() * 2 for x in xs)
     d2h = out_dev.numel() * 2
@@ -463,6 +475,7 @@ def run_gpu_arm(args) -> None:
                 "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(t.item()) * 1e3,
                 "steps": e2e_steps,
+                "passes": e2e_passes,
                 "path": "conch_b200.mixed_precision_gemm called 128x per step from Python, pinned-host x -> device, outputs -> pinned host",
             },
             "gpu_launches": launches_per_step * args.steps,
