@@ -286,7 +286,8 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
     // register-window kernel (bf16 x int8, group sizes that straddle stages); tcgen05 pipeline above.
     // (M = 9..16: the streaming kernel's 16-row variant where it has a format for the problem -- 3 to 17 % ahead of the tcgen05
     //  kernel on the four Llama-3-8B shapes, profiles/r02_decode_table_m16.log; otherwise tcgen05, as for everything above)
-    const bool decode = M <= 8 || (M <= 16 && stream_supported(p, weight_size_bits, act_dtype));
+    //  8-bit weights keep M = 9..16 on tcgen05: twice the MMAs per weight, 56 against 48 us on gate_up, profiles/r02_config4_*.log)
+    const bool decode = M <= 8 || (M <= 16 && weight_size_bits == 4 && stream_supported(p, weight_size_bits, act_dtype));
     if (decode || !tc_supported(p, weight_size_bits)) {
       // (fused gather: the streaming kernel for any number of peers -- 8 GPUs, 128 pushing GEMVs per token: 1.35 ms against 1.84 ms
       //  on the register-window kernel and 1.31 ms without any push, profiles/r02_push_modes_n8.log)

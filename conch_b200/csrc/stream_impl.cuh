@@ -135,15 +135,21 @@ __device__ __forceinline__ void mma_zero(float (&d)[4], uint32_t a0, uint32_t a1
 //   bf16 x int4 : 0x4300 | q = 128 + q (a bf16 significand holds 8 bits), one shift per nibble position; the 128 is taken out
 //                 with the zero-point: G = P + Q, correction -(128 + zb) * X
 //   fp16 x int8 : bytes become q * 2^-24; one MMA per 16-column tile and quad (a quad is 16 k), P only
+//   bf16 x int8 : a byte does not fit a bf16 significand, its two NIBBLES do: q = lo + 16 hi, both planes as 0x4300 | nibble
+//                 (the bf16 x int4 extraction applied to a word of 4 bytes yields (lo k0, lo k2), (hi k0, hi k2), (lo k1, lo k3),
+//                 (hi k1, hi k3)); P takes the low plane, Q the high one against the SAME activations: G = P + 16 Q, and the
+//                 128 (1 + 16) = 2176 X that the magic operands add goes out with the zero-point.  Two MMAs per byte pair -- the
+//                 int4 rate per byte of weights
 template <class A, int BITS>
 struct Fmt {
   static constexpr bool HALF = std::is_same<A, __half>::value;
   static constexpr int PF = 32 / BITS;                 // k per packed word
   static constexpr int XQ = 4 * PF * 2;                // bytes of one x row per quad (4 packed rows)
   static constexpr int CPQ = XQ / 16;                  // 16-byte chunks of x per quad and row
-  static constexpr bool HAS_Q = BITS == 4;             // second accumulator set
-  static constexpr float QSCALE = HALF ? 0.0625f : 1.f;
-  static constexpr float MAGIC = HALF ? 0.f : 128.f;
+  static constexpr bool NIB8 = !HALF && BITS == 8;     // bf16 x int8: two nibble planes
+  static constexpr bool HAS_Q = BITS == 4 || NIB8;     // second accumulator set
+  static constexpr float QSCALE = HALF ? 0.0625f : NIB8 ? 16.f : 1.f;
+  static constexpr float MAGIC = HALF ? 0.f : NIB8 ? 2176.f : 128.f;
   static constexpr float OPSCALE = HALF ? 16777216.f : 1.f;
 };
 
@@ -156,9 +162,9 @@ struct Accum {
 
 // One quad: this lane's 4 packed words (4 columns, packed row 4 * quad + t) against its activations.
 //   int4: xv[mt] = the lane's 8 activations permuted to {(k0,k4), (k2,k6), (k1,k5), (k3,k7)}
-//   int8: xv[mt].x/.y = (k0,k1), (k2,k3)
+//   int8: xv[mt].x/.y = (k0,k1), (k2,k3) -- bf16 x int8: (k0,k2), (k1,k3)
 template <class A, int BITS, int MT, bool FRESH>
-__device__ __forceinline__ void quad_math(Accum<MT, BITS == 4>& a, const uint4 wv, const uint4 (&xv)[MT]) {
+__device__ __forceinline__ void quad_math(Accum<MT, Fmt<A, BITS>::HAS_Q>& a, const uint4 wv, const uint4 (&xv)[MT]) {
   using F = Fmt<A, BITS>;
   const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
   if constexpr (MT > 1) {
@@ -173,7 +179,7 @@ __device__ __forceinline__ void quad_math(Accum<MT, BITS == 4>& a, const uint4 w
       if constexpr (BITS == 4) mma_acc<A>(a.XS[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].z, xv[mt].w);
     }
   }
-  if constexpr (BITS == 4) {
+  if constexpr (BITS == 4 || F::NIB8) {
     uint32_t d[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -192,12 +198,14 @@ __device__ __forceinline__ void quad_math(Accum<MT, BITS == 4>& a, const uint4 w
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int tl = 0; tl < 2; ++tl) {
+        // (int4: the odd nibbles belong to the second half of the lane's 8 activations; bf16 x int8: the high nibbles of the same 4)
+        const uint32_t qx0 = F::NIB8 ? xv[mt].x : xv[mt].z, qx1 = F::NIB8 ? xv[mt].y : xv[mt].w;
         if constexpr (FRESH) {
           mma_zero<A>(a.P[mt][tl], d[2 * tl][0], d[2 * tl + 1][0], d[2 * tl][2], d[2 * tl + 1][2], xv[mt].x, xv[mt].y);
-          mma_zero<A>(a.Q[mt][tl], d[2 * tl][1], d[2 * tl + 1][1], d[2 * tl][3], d[2 * tl + 1][3], xv[mt].z, xv[mt].w);
+          mma_zero<A>(a.Q[mt][tl], d[2 * tl][1], d[2 * tl + 1][1], d[2 * tl][3], d[2 * tl + 1][3], qx0, qx1);
         } else {
           mma_acc<A>(a.P[mt][tl], d[2 * tl][0], d[2 * tl + 1][0], d[2 * tl][2], d[2 * tl + 1][2], xv[mt].x, xv[mt].y);
-          mma_acc<A>(a.Q[mt][tl], d[2 * tl][1], d[2 * tl + 1][1], d[2 * tl][3], d[2 * tl + 1][3], xv[mt].z, xv[mt].w);
+          mma_acc<A>(a.Q[mt][tl], d[2 * tl][1], d[2 * tl + 1][1], d[2 * tl][3], d[2 * tl + 1][3], qx0, qx1);
         }
       }
   } else {
@@ -429,6 +437,11 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
             o.y = prmt(v[u].y, v[u].w, 0x5410u);
             o.z = prmt(v[u].x, v[u].z, 0x7632u);
             o.w = prmt(v[u].y, v[u].w, 0x7632u);
+          } else if constexpr (F::NIB8) {  // two words' worth per chunk: (k0,k1),(k2,k3) -> (k0,k2),(k1,k3)
+            o.x = prmt(v[u].x, v[u].y, 0x5410u);
+            o.y = prmt(v[u].x, v[u].y, 0x7632u);
+            o.z = prmt(v[u].z, v[u].w, 0x5410u);
+            o.w = prmt(v[u].z, v[u].w, 0x7632u);
           }
           sts128(xs + mm[u] * geo.x_pitch + (cv[u] - c_lo) * 16, o);
           const uint32_t r[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
@@ -569,7 +582,8 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
         }
       } else {
         const uint2 v = lds64(lane_x[mt] + quad * F::XQ);
-        xv[mt] = make_uint4(v.x, v.y, 0u, 0u);
+        if constexpr (MT > 1 && F::NIB8) xv[mt] = make_uint4(prmt(v.x, v.y, 0x5410u), prmt(v.x, v.y, 0x7632u), 0u, 0u);  // raw window
+        else xv[mt] = make_uint4(v.x, v.y, 0u, 0u);
       }
     }
   };
@@ -813,5 +827,6 @@ static int launch_stream_typed(const CUtensorMap& mw, const Problem& p, const St
 CB200_STREAM_ENTRY(launch_stream_f16_w4);
 CB200_STREAM_ENTRY(launch_stream_f16_w8);
 CB200_STREAM_ENTRY(launch_stream_bf16_w4);
+CB200_STREAM_ENTRY(launch_stream_bf16_w8);
 
 }  // namespace cb200

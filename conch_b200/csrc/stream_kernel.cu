@@ -51,7 +51,7 @@ static int stream_sms() {
 
 bool stream_supported(const Problem& p, int bits, int act_dtype) {
   if (encode_fn() == nullptr) return false;
-  if (act_dtype == CB200_BF16 && bits == 8) return false;  // no magic-number operand: decode_kernel's per-weight dequant
+  (void)act_dtype;  // (bf16 x int8 runs as two nibble planes since round 2)
   const int quad_k = 4 * (32 / bits);                      // k per quad (4 packed rows)
   if (p.K % quad_k != 0 || p.N % 32 != 0 || p.g % quad_k != 0) return false;
   const int qpg = p.g / quad_k;
@@ -227,7 +227,8 @@ int launch_stream(const Problem& p_in, int bits, int act_dtype, void* ws, size_t
       rc = bits == 4 ? launch_stream_f16_w4(*mw, p, geo, pl.grid, pl.smem, pdl, stream)
                      : launch_stream_f16_w8(*mw, p, geo, pl.grid, pl.smem, pdl, stream);
     } else {
-      rc = launch_stream_bf16_w4(*mw, p, geo, pl.grid, pl.smem, pdl, stream);
+      rc = bits == 4 ? launch_stream_bf16_w4(*mw, p, geo, pl.grid, pl.smem, pdl, stream)
+                     : launch_stream_bf16_w8(*mw, p, geo, pl.grid, pl.smem, pdl, stream);
     }
     if (rc != 0) return rc;
     if (launches) ++*launches;

@@ -45,16 +45,17 @@ def _case(m, k, n, wname, g, dtype, zp, seed=0, zp_as=None, out_dtype=None, reci
 
 @pytest.mark.parametrize("m", [1, 2, 3, 5, 8, 9, 13, 16])
 @pytest.mark.parametrize("dtype,wname", [(torch.float16, "uint4"), (torch.float16, "uint4b8"), (torch.float16, "uint8"),
-                                         (torch.float16, "uint8b128"), (torch.bfloat16, "uint4"), (torch.bfloat16, "uint4b8")],
-                         ids=["f16-u4", "f16-u4b8", "f16-u8", "f16-u8b128", "bf16-u4", "bf16-u4b8"])  # fmt: skip
+                                         (torch.float16, "uint8b128"), (torch.bfloat16, "uint4"), (torch.bfloat16, "uint4b8"),
+                                         (torch.bfloat16, "uint8"), (torch.bfloat16, "uint8b128")],
+                         ids=["f16-u4", "f16-u4b8", "f16-u8", "f16-u8b128", "bf16-u4", "bf16-u4b8", "bf16-u8", "bf16-u8b128"])  # fmt: skip
 def test_rows_and_formats(m, dtype, wname):
     out, want, _ = _case(m, 1024, 512, wname, 128, dtype, True)
     assert_gemm_close(out, want, f"M={m} {wname} {dtype}")
 
 
 def test_auto_dispatch_and_unsupported_formats():
-    """AUTO: the streaming kernel up to 8 rows where it has an operand format and a stage layout for the problem, round 1's
-    register-window kernel for the rest of the decode regime (bf16 x int8, group sizes that straddle a stage), tcgen05 above."""
+    """AUTO: the streaming kernel up to 16 rows where it has a stage layout for the problem, round 1's register-window kernel
+    for the rest up to 8 rows (group sizes that straddle a stage), tcgen05 above."""
     lib = _lib.load()
 
     def auto(m, k, n, wname, g, dtype):
@@ -69,12 +70,14 @@ def test_auto_dispatch_and_unsupported_formats():
     assert auto(9, 512, 256, "uint4", 128, torch.float16) == STREAM  # 16-row variant
     assert auto(16, 512, 256, "uint4", 128, torch.float16) == STREAM
     assert auto(17, 512, 256, "uint4", 128, torch.float16) == _lib.TC_TS
-    assert auto(12, 512, 256, "uint8", 128, torch.bfloat16) == _lib.TC_TS  # no streaming format: tcgen05 above 8 rows
+    assert auto(8, 512, 256, "uint8", 128, torch.bfloat16) == STREAM
+    assert auto(12, 512, 256, "uint8", 128, torch.float16) == _lib.TC_TS  # 8-bit weights: tcgen05 above 8 rows
+    assert auto(12, 768, 256, "uint4", 192, torch.float16) == _lib.TC_TS  # no streaming stage layout: tcgen05 above 8 rows
     assert auto(4, 512, 256, "uint8", 128, torch.float16) == STREAM
     assert auto(4, 512, 256, "uint4b8", -1, torch.bfloat16) == STREAM
-    assert auto(4, 512, 256, "uint8", 128, torch.bfloat16) == _lib.DECODE_MMA  # 128 + q does not fit a bf16 significand
+    assert auto(4, 512, 256, "uint8", 128, torch.bfloat16) == STREAM  # (two nibble planes: a byte does not fit a bf16 significand)
     assert auto(4, 768, 256, "uint4", 192, torch.float16) == _lib.DECODE_MMA   # 6 quads per group: straddles the 4-quad stages
-    for wname, g, dtype, k in (("uint8", 128, torch.bfloat16, 512), ("uint4", 192, torch.float16, 768)):
+    for wname, g, dtype, k in (("uint4", 192, torch.float16, 768),):
         p = oracle.make_problem(4, k, 256, wname, g, dtype, True, seed=0)
         x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
         with pytest.raises(NotImplementedError):
@@ -128,17 +131,18 @@ def test_llama3_8b_decode_shapes(k, n, m):
 
 
 @pytest.mark.parametrize("wname,g,dtype", [("uint8", 128, torch.float16), ("uint8b128", 128, torch.float16),
-                                           ("uint4", -1, torch.bfloat16), ("uint4b8", -1, torch.bfloat16)])  # fmt: skip
+                                           ("uint4", -1, torch.bfloat16), ("uint4b8", -1, torch.bfloat16),
+                                           ("uint8", 128, torch.bfloat16), ("uint8b128", -1, torch.bfloat16)])  # fmt: skip
 @pytest.mark.parametrize("m", [1, 16])
 def test_config4_formats_at_llama_size(wname, g, dtype, m):
-    """BASELINE config 4 (W8A16, per-channel int4 with bf16) on the 4096 x 4096 projection.  bf16 x int8 is the register-window
-    kernel's (AUTO), so W8A16 is checked with fp16 here and with bf16 in test_gpu_parity.py."""
+    """BASELINE config 4 (W8A16, per-channel int4 with bf16) on the 4096 x 4096 projection."""
     out, want, _ = _case(m, 4096, 4096, wname, g, dtype, wname in ("uint8", "uint4"))
     assert_gemm_close(out, want)
 
 
 @pytest.mark.parametrize("dtype,wname,zp", [(torch.float16, "uint4", True), (torch.float16, "uint4b8", False),
-                                            (torch.float16, "uint8", True), (torch.bfloat16, "uint4", True)])  # fmt: skip
+                                            (torch.float16, "uint8", True), (torch.bfloat16, "uint4", True),
+                                            (torch.bfloat16, "uint8", True), (torch.bfloat16, "uint8b128", False)])  # fmt: skip
 def test_one_hot_rows_reproduce_the_reference_weights_bit_for_bit(dtype, wname, zp):
     """x = e_k selects row k of W: the per-group fp32 correction s*q - s*zb is exact, so the single rounding to the output
     dtype is the reference's (conch/kernels/quantization/gemm.py:205-216)."""
