@@ -358,7 +358,7 @@ def run_gpu_arm(args) -> None:
     col0 = [0]
     for _, _, n in PROJECTIONS:
         col0.append(col0[-1] + n)
-    out_views = [[out_dev[layer : layer + 1, col0[pi] : col0[pi + 1]] for pi in range(len(PROJECTIONS))] for layer in range(LAYERS)]
+    out_views = [[out_dev[layer : layer + 1, col0[pi] : col0[pi + 1]].view(M, -1) for pi in range(len(PROJECTIONS))] for layer in range(LAYERS)]
     # column slices of a row-major buffer are not contiguous for M>1, but with M=1 each view is one dense row segment
     x_dev = [torch.empty_like(x) for x in xs]
 
@@ -370,14 +370,14 @@ def run_gpu_arm(args) -> None:
             for pi in range(len(PROJECTIONS)):
                 packed, w_s, w_zp = weights[layer][pi]
                 if world > 1 and args.nccl_gather:
-                    _, work = sharded[layer][pi].gathered_async(x_dev[pi], out=out_views[layer][pi].view(M, -1))
+                    _, work = sharded[layer][pi].gathered_async(x_dev[pi], out=out_views[layer][pi])
                     if pending is not None:
                         pending.wait()
                     pending = work
                 elif world > 1:
                     sharded[layer][pi].pushed(x_dev[pi], variant=push_variant)
                 else:
-                    mixed_precision_gemm(x_dev[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=out_views[layer][pi].view(M, -1))
+                    mixed_precision_gemm(x_dev[pi], packed, w_s, w_zp, BITS, BIAS, GROUP, out=out_views[layer][pi])
         if pending is not None:
             pending.wait()
         if world > 1 and not args.nccl_gather:

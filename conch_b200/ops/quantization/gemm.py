@@ -12,12 +12,15 @@ There is no CPU / Triton fallback: inputs must live on a B200.
 
 from __future__ import annotations
 
+import ctypes
+import weakref
 from collections.abc import Sequence
 from typing import Final
 
 import torch
 
 from conch_b200 import _lib
+from conch_b200.kernels.quantization import gemm as _kernels_gemm
 from conch_b200.kernels.quantization.gemm import (
     ChannelScaleMode,
     dequantize_launcher,
@@ -198,12 +201,32 @@ def mixed_precision_gemm(
     the separate `output.add_(bias)` kernel a caller of the reference op runs (the reference's sibling op does exactly that,
     conch/ops/quantization/gemm.py:249-250).
     """
+    # ---- repeat calls on the same weight tensors (a decode loop): everything that depends on the weights alone was validated
+    # and resolved by the first call; only x / out are looked at again.  4-5 us of host time instead of 11 -- at M=1 the GEMVs of
+    # a Llama-3-8B token take 9.7 us each on the device, so the full path is what an eager caller would wait for.
+    # (peer pointers ride along when the caller hands them over as a ready C array: conch_b200/sharded.py pushed())
+    plain = (output_dtype is None and bias is None and signal is None and x_ready is None and acc_dtype is None
+             and meta_dtype is None and not strict and (peer_out_ptrs is None or isinstance(peer_out_ptrs, ctypes.Array)))  # fmt: skip
+    if plain:
+        e = _fast_entries.get(id(w_q_packed))
+        if (e is not None and e[0]() is w_q_packed and e[1] is w_s and e[2] is w_zp and e[3] == weight_size_bits
+                and e[4] == weight_bias and e[5] == group_size and x.dtype is e[6] and x.dim() == 2 and x.is_contiguous()
+                and x.device == e[7]):  # fmt: skip
+            m_dim, k_dim = x.shape
+            if k_dim == e[8] and m_dim > 0:
+                if out is None:
+                    out = torch.empty((m_dim, e[9]), device=e[7], dtype=e[6])
+                elif out.dim() != 2 or out.shape[0] != m_dim or out.shape[1] != e[9] or out.dtype is not e[6] or not out.is_contiguous():
+                    raise ValueError("`out` must be a contiguous [M, N] tensor of the output dtype")
+                if _fast_launch(e, x, out, m_dim, variant, peer_out_ptrs):
+                    return out
     _require_device(x, w_q_packed, w_s, w_zp)
     metadata = create_mixed_precision_metadata(
         x, w_q_packed, w_s, w_zp, weight_size_bits, weight_bias, group_size,
         output_dtype=output_dtype, acc_dtype=acc_dtype, meta_dtype=meta_dtype,
         scaled_activations=scaled_activations, strict=strict,
     )  # fmt: skip
+    register = plain and metadata.data_contiguous and metadata.m_dim > 0
     if not metadata.data_contiguous:
         # the reference honours arbitrary strides (gemm.py:518-525); the CUDA kernels want dense row-major
         x, w_q_packed, w_s = x.contiguous(), w_q_packed.contiguous(), w_s.contiguous()
@@ -232,7 +255,60 @@ def mixed_precision_gemm(
             out, _dense_aligned(x), _dense_aligned(w_q_packed), _dense_aligned(w_s), None if w_zp is None else _dense_aligned(w_zp),
             metadata, variant=variant, peer_out_ptrs=peer_out_ptrs, signal=signal, x_ready=x_ready, bias=bias,
         )  # fmt: skip
+        register = False
+    if register:
+        _fast_register(x, w_q_packed, w_s, w_zp, metadata, group_size)
     return out
+
+
+# id(w_q_packed) -> (weakref(w_q_packed), w_s, w_zp, bits, bias, group_size as passed, dtype, device, K, N, resolved group size,
+#                    zero-point kind, zero_is_scalar, dtype code, device index); dropped when the packed tensor dies
+_fast_entries: dict[int, tuple] = {}
+
+
+def _fast_register(x, w_q_packed, w_s, w_zp, metadata: MixedPrecisionMatmulMetadata, group_size_arg: int) -> None:
+    from conch_b200.kernels.quantization.gemm import _DTYPE_CODE, zero_point_kind
+
+    key = id(w_q_packed)
+    try:
+        ref = weakref.ref(w_q_packed, lambda _r, key=key: _fast_entries.pop(key, None))
+    except TypeError:  # (a tensor subclass without weak references: no fast path)
+        return
+    if len(_fast_entries) > 4096:
+        _fast_entries.clear()
+    device = x.device
+    _fast_entries[key] = (
+        ref, w_s, w_zp, metadata.weight_size_bits, metadata.weight_bias, group_size_arg, metadata.input_dtype, device,
+        metadata.k_dim, metadata.n_dim, metadata.group_size, zero_point_kind(x, w_zp), int(metadata.zero_is_scalar),
+        _DTYPE_CODE[metadata.input_dtype], device.index if device.index is not None else torch.cuda.current_device(),
+    )  # fmt: skip
+
+
+def _fast_launch(e: tuple, x: torch.Tensor, out: torch.Tensor, m_dim: int, variant: int, peers=None) -> bool:
+    """The launcher without its bookkeeping; False sends the call down the full path (which also words the errors)."""
+    kg = _kernels_gemm
+    index = e[14]
+    if index != torch.cuda.current_device():
+        return False
+    lib = _lib.load()
+    stream = kg._raw_stream(index)
+    ws = kg._workspaces.get((index, stream))
+    if ws is None:
+        return False
+    w_zp = e[2]
+    code = e[13]
+    if peers is None:
+        rc = lib.cb200_mpgemm(
+            x.data_ptr(), e[0]().data_ptr(), e[1].data_ptr(), None if w_zp is None else w_zp.data_ptr(), out.data_ptr(),
+            m_dim, e[8], e[9], e[3], e[4], e[10], code, code, e[11], e[12], ws.data_ptr(), ws.numel(), variant, stream,
+        )  # fmt: skip
+    else:
+        rc = lib.cb200_mpgemm_push(
+            x.data_ptr(), e[0]().data_ptr(), e[1].data_ptr(), None if w_zp is None else w_zp.data_ptr(), out.data_ptr(),
+            m_dim, e[8], e[9], e[3], e[4], e[10], code, code, e[11], e[12], ws.data_ptr(), ws.numel(), variant, stream,
+            peers, len(peers),
+        )  # fmt: skip
+    return rc == 0
 
 
 class PreparedWeights:

@@ -66,6 +66,7 @@ class ShardedMixedPrecisionLinear:
         self._local_buf: torch.Tensor | None = None
         self._symm: dict[tuple[int, torch.dtype], tuple[torch.Tensor, object, list[int]]] = {}
         self._flags: tuple[torch.Tensor, object, list[int]] | None = None
+        self._push_fast: dict[tuple[int, torch.dtype], tuple[torch.Tensor, object]] = {}
 
     def local(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         """This rank's `[M, N/G]` slice of the output (no communication)."""
@@ -290,8 +291,13 @@ class ShardedMixedPrecisionLinear:
             raise NotImplementedError(f"pushed() is for the decode regime (M <= {self.PUSH_MAX_ROWS}); use gathered() for M={m}")
         out_dtype = kwargs.get("output_dtype") or x.dtype
         buf, _, peers = self._symmetric(m, out_dtype, x.device)
+        fast = self._push_fast.get((m, out_dtype))
+        if fast is None:  # this rank's slot as a tensor and the peer pointers as a C array, made once per (M, dtype)
+            import ctypes
+
+            fast = self._push_fast[(m, out_dtype)] = (buf[self.rank], (ctypes.c_void_p * len(peers))(*peers))
         self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size,
-                   out=buf[self.rank], peer_out_ptrs=peers, **kwargs)  # fmt: skip
+                   out=fast[0], peer_out_ptrs=fast[1], **kwargs)  # fmt: skip
         return buf
 
     def pushed_local_view(self, m: int, dtype: torch.dtype = torch.float16) -> torch.Tensor:

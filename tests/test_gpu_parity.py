@@ -525,3 +525,35 @@ def test_decode_group_sums_prologue(m, dtype, wname, zp, g):
         _run_case(m, 4096, 192, wname, g, dtype, zp, variant=_lib.DECODE_MMA, zp_as=torch.uint8 if zp else None)
     finally:
         lib.cb200_set_decode_tuning(0, 0, 0, 0)
+
+
+def test_repeat_calls_take_the_fast_path_and_stay_correct():
+    """The op remembers what it validated about a set of weight tensors (conch_b200/ops/quantization/gemm.py, _fast_entries):
+    repeat calls skip the metadata pass.  Same results, same errors, and nothing is reused for different tensors."""
+    import gc
+
+    from conch_b200.ops.quantization import gemm as og
+
+    p = oracle.make_problem(3, 512, 256, "uint4", 128, torch.float16, True, seed=11)
+    x, wq, ws, wzp = to_cuda(p.x, p.w_q_packed, p.w_s, p.w_zp)
+    y1 = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128)
+    assert id(wq) in og._fast_entries
+    y2 = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128)
+    out = torch.empty_like(y1)
+    y3 = mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, out=out)
+    assert y3 is out and torch.equal(bits(y1), bits(y2)) and torch.equal(bits(y1), bits(y3))
+    assert_gemm_close(y2, oracle.mixed_precision_gemm_ref(p.x, p.w_q_packed, p.w_s, p.w_zp, 4, 0, 128))
+    assert torch.equal(bits(mixed_precision_gemm(x[:1].contiguous(), wq, ws, wzp, 4, 0, 128)), bits(y1[:1]))  # another M
+    y4 = mixed_precision_gemm(x, wq, ws * 2, wzp, 4, 0, 128)  # other scales with the same packed tensor: not the remembered entry
+    torch.testing.assert_close(y4.float(), 2 * y1.float(), rtol=2e-3, atol=2e-3)
+    with pytest.raises(ValueError):
+        mixed_precision_gemm(x[:, :256].contiguous(), wq, ws, wzp, 4, 0, 128)  # K mismatch: full validation words the error
+    with pytest.raises(ValueError):
+        mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, out=torch.empty((3, 256), device="cuda", dtype=torch.float32))
+    with pytest.raises(ValueError):
+        mixed_precision_gemm(x, wq, ws[:2], wzp, 4, 0, 128)
+    assert mixed_precision_gemm(x, wq, ws, wzp, 4, 0, 128, output_dtype=torch.float32).dtype == torch.float32  # keyword: full path
+    key = id(wq)
+    del wq, y1, y2, y3, y4
+    gc.collect()
+    assert key not in og._fast_entries
