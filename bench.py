@@ -362,6 +362,11 @@ def run_gpu_arm(args) -> None:
     # column slices of a row-major buffer are not contiguous for M>1, but with M=1 each view is one dense row segment
     x_dev = [torch.empty_like(x) for x in xs]
 
+    local_views = None  # (N > 1) this rank's slots of the 128 gather buffers: they exist after the steps above
+    if world > 1 and not args.nccl_gather:
+        local_views = [sharded[layer][pi].pushed_local_view(M) for layer in range(LAYERS) for pi in range(len(PROJECTIONS))]
+    out_flat = out_dev.view(1, -1)
+
     def e2e_step():
         for pi in range(len(PROJECTIONS)):
             x_dev[pi].copy_(x_host[pi], non_blocking=True)
@@ -383,8 +388,7 @@ def run_gpu_arm(args) -> None:
         if world > 1 and not args.nccl_gather:
             sharded[0][0].sync()
             # this rank's own slices (the result it computed) go back to the host, like the single-GPU arm
-            torch.cat([sharded[layer][pi].pushed_local_view(M) for layer in range(LAYERS) for pi in range(len(PROJECTIONS))],
-                      dim=1, out=out_dev.view(1, -1))
+            torch.cat(local_views, dim=1, out=out_flat)
         out_host.copy_(out_dev, non_blocking=True)
 
     e2e_steps = max(3, min(args.steps, 50))

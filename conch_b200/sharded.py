@@ -66,7 +66,7 @@ class ShardedMixedPrecisionLinear:
         self._local_buf: torch.Tensor | None = None
         self._symm: dict[tuple[int, torch.dtype], tuple[torch.Tensor, object, list[int]]] = {}
         self._flags: tuple[torch.Tensor, object, list[int]] | None = None
-        self._push_fast: dict[tuple[int, torch.dtype], tuple[torch.Tensor, object]] = {}
+        self._push_fast: dict[tuple[int, torch.dtype], tuple[torch.Tensor, object, torch.Tensor]] = {}
 
     def local(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         """This rank's `[M, N/G]` slice of the output (no communication)."""
@@ -285,6 +285,11 @@ class ShardedMixedPrecisionLinear:
         next token while a peer may still read it needs a second `sync()` -- the caller's protocol.  M <= 8 only
         (decode regime); larger M should use `gathered()` (bandwidth-bound: NCCL is the right tool)."""
         m = x.shape[0]
+        if not kwargs:  # the decode loop's call: everything below was resolved by the first call with this (M, dtype)
+            fast = self._push_fast.get((m, x.dtype))
+            if fast is not None:
+                self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size, out=fast[0], peer_out_ptrs=fast[1])
+                return fast[2]
         if self.world == 1:
             return self.local(x, **kwargs).unsqueeze(0)
         if m > self.PUSH_MAX_ROWS:
@@ -295,7 +300,7 @@ class ShardedMixedPrecisionLinear:
         if fast is None:  # this rank's slot as a tensor and the peer pointers as a C array, made once per (M, dtype)
             import ctypes
 
-            fast = self._push_fast[(m, out_dtype)] = (buf[self.rank], (ctypes.c_void_p * len(peers))(*peers))
+            fast = self._push_fast[(m, out_dtype)] = (buf[self.rank], (ctypes.c_void_p * len(peers))(*peers), buf)
         self._gemm(x, self.w_q_packed, self.w_s, self.w_zp, self.bits, self.bias, self.group_size,
                    out=fast[0], peer_out_ptrs=fast[1], **kwargs)  # fmt: skip
         return buf
@@ -319,6 +324,8 @@ class ShardedMixedPrecisionLinear:
         if self.world == 1:
             return g[0]
         m = g.shape[1]
+        # a fresh tensor for every M (for M = 1 the buffer itself is [1, N] in memory, but a view of it would be overwritten by the
+        # next call on this layer while M > 1 returns a copy: same ownership either way)
         if m == 1:
-            return g.reshape(1, self.n_total)  # [G, 1, N/G] is already [1, N] in memory
+            return g.reshape(1, self.n_total).clone()
         return g.permute(1, 0, 2).reshape(m, self.n_total)
