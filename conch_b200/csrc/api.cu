@@ -283,7 +283,7 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
   if (chosen == CB200_AUTO) {
     // regime split by MEASUREMENT (profiles/r02_*): HBM-bound skinny GEMM up to 8 rows (one 8-wide MMA tile of x) on the
     // streaming ring kernel where it has an operand format and a stage layout for the problem, else on round 1's
-    // register-window kernel (bf16 x int8, group sizes that straddle stages); tcgen05 pipeline above.
+    // register-window kernel (group sizes that straddle stages); tcgen05 pipeline above.
     // (M = 9..16: the streaming kernel's 16-row variant where it has a format for the problem -- 3 to 17 % ahead of the tcgen05
     //  kernel on the four Llama-3-8B shapes, profiles/r02_decode_table_m16.log; otherwise tcgen05, as for everything above)
     //  8-bit weights keep M = 9..16 on tcgen05: twice the MMAs per weight, 56 against 48 us on gate_up, profiles/r02_config4_*.log)
@@ -315,7 +315,7 @@ static int run_mpgemm(const void* x, const void* w_q_packed, const void* w_s, co
     rc = launch_decode(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);
   } else if (chosen == CB200_DECODE_STREAM) {
     if (!stream_supported(p, weight_size_bits, act_dtype)) {
-      set_error("the streaming decode kernel does not support this problem (bf16 x int8, or a group size that is neither 1, 2 nor a multiple of 4 quads of packed rows: use CB200_DECODE_MMA)");
+      set_error("the streaming decode kernel does not support this problem (a group size that is neither 1, 2 nor a multiple of 4 quads of packed rows: use CB200_DECODE_MMA)");
       return CB200_ERR_UNSUPPORTED;
     }
     rc = launch_stream(p, weight_size_bits, act_dtype, workspace, workspace_bytes, st, &launches);

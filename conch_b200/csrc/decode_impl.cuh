@@ -543,7 +543,8 @@ template <class A, int BITS, int MT, int U, int ZK>
 static int launch_fused(bool fused, const Problem& p, const DecodeGeom& geo, int blocks, size_t smem, float* wsp,
                         unsigned* wsc, cudaStream_t stream) {
   void (*kern)(const Problem, const DecodeGeom, float*, unsigned int*);
-  // bf16 x int8: 128 + q does not fit a bf16 significand, so there is no magic-number operand -> per-weight dequant
+  // bf16 x int8: 128 + q does not fit a bf16 significand, so THIS kernel has no magic-number operand -> per-weight dequant
+  // (the streaming kernel, AUTO's choice, splits the byte into two nibble planes instead)
   if (fused && !(std::is_same<A, __nv_bfloat16>::value && BITS == 8)) {
     kern = decode_kernel<A, BITS, MT, U, ZK, true>;
     if constexpr (MT == 1) {

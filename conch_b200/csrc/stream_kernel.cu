@@ -1,8 +1,8 @@
 // Streaming ("ring") decode kernel (CB200_DECODE_STREAM, AUTO's choice for M <= 8): host-side plan and dispatch.
 //
 // Replaces the reference's single 128x64x64 Triton tile (conch/kernels/quantization/gemm.py:136-145, 491-494), which at M=1
-// launches N/64 CTAs with no split-K, and supersedes round 1's register-window kernel (decode_kernel.cu, kept for bf16 x int8,
-// odd group sizes and the per-weight-dequant variant) as the default decode path.
+// launches N/64 CTAs with no split-K, and supersedes round 1's register-window kernel (decode_kernel.cu, kept for odd group sizes
+// and the per-weight-dequant variant) as the default decode path.
 //
 // Shape of the kernel (stream_impl.cuh), each item from a measurement (profiles/r02_ring_*.log):
 //   * ONE CTA per SM, warp specialised: a producer warp + 2..4 groups of consumer warps (12-16 consumer warps in all).  The

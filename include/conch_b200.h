@@ -58,16 +58,16 @@ enum cb200_zp_kind { CB200_ZP_NONE = 0, CB200_ZP_I32 = 1, CB200_ZP_U8 = 2, CB200
 /* kernel families; 0 lets the library choose by regime */
 enum cb200_variant {
   CB200_AUTO = 0,
-  CB200_DECODE_MMA = 1,   /* <= 16 rows per pass (AUTO: M <= 8): split-K skinny GEMM, 128-bit weight loads, in-register unpack, HMMA dot, last-arriver reduce */
+  CB200_DECODE_MMA = 1,   /* <= 16 rows per pass (AUTO: M <= 8 where CB200_DECODE_STREAM has no stage layout for the problem): split-K skinny GEMM, 128-bit weight loads, in-register unpack, HMMA dot, last-arriver reduce */
   CB200_TC_SS = 2,        /* tcgen05: TMA -> smem dequant (K-major, 128B swizzle) -> UMMA (both operands smem), TMEM accumulators */
   CB200_TC_TS = 3,        /* tcgen05: TMA -> dequant straight into TMEM (W is the TMEM A operand), x tile from smem */
   CB200_TC2_TS = 4,       /* persistent tcgen05 kernel: m_tile 128, two TMEM accumulators, epilogue overlaps the next tile */
-  CB200_DECODE_STREAM = 5 /* <= 16 rows per pass (AUTO: M <= 16 where it has an operand format for the problem): warp-specialised streaming GEMV -- a producer warp keeps a ring of TMA weight
-                             tiles in shared memory full (it never waits for the stream order: under programmatic dependent launch
+  CB200_DECODE_STREAM = 5 /* <= 16 rows per pass (AUTO: M <= 8, and M <= 16 for 4-bit weights): warp-specialised streaming GEMV -- a
+                             producer warp keeps a ring of TMA weight tiles in shared memory full (it never waits for the stream order: under programmatic dependent launch
                              the ring fills while the previous kernel drains), 12-16 consumer warps turn nibbles into subnormal fp16
                              MMA operands, K is split over a thread-block cluster whose partial sums meet in distributed shared
-                             memory (no workspace, no atomics, deterministic).  bf16 x int8 and group sizes that straddle a
-                             16-packed-row stage are left to CB200_DECODE_MMA. */
+                             memory (no workspace, no atomics, deterministic).  bf16 x int8 runs as two nibble planes.  Group
+                             sizes that straddle a 16-packed-row stage (e.g. int4 groups of 192) are left to CB200_DECODE_MMA. */
 };
 
 enum cb200_status {
