@@ -43,6 +43,8 @@ def _worker(rank: int, world: int, port: int, m: int, wname: str, zp: bool, scal
         out = layer(p.x)
         assert out.shape == (m, 256)
         assert torch.equal(out, full)
+        out2 = layer(-p.x)  # the next call must not overwrite what the previous one returned (M = 1 used to be a view)
+        assert torch.equal(out, full) and out2.data_ptr() != out.data_ptr()
         g = layer.gathered(p.x)
         assert g.shape == (world, m, 128) and torch.equal(g[1 - rank], full[:, (1 - rank) * 128 : (2 - rank) * 128])
         ga, work = layer.gathered_async(p.x)  # enqueue only; the view is valid after the wait
