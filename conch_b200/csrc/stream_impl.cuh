@@ -158,6 +158,7 @@ struct Accum {
   float P[MT][2][4];
   float Q[HAS_Q ? MT : 1][2][4];
   float XS[MT][4];  // 16-row variant only: sums of x over the open scale group, by an MMA against an all-ones operand
+  float XT[MT][4];  //   (int4: the second half of the lane's activations accumulates here -- two chains of half the length)
 };
 
 // One quad: this lane's 4 packed words (4 columns, packed row 4 * quad + t) against its activations.
@@ -176,7 +177,10 @@ __device__ __forceinline__ void quad_math(Accum<MT, Fmt<A, BITS>::HAS_Q>& a, con
     for (int mt = 0; mt < MT; ++mt) {
       if constexpr (FRESH) mma_zero<A>(a.XS[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].x, xv[mt].y);
       else mma_acc<A>(a.XS[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].x, xv[mt].y);
-      if constexpr (BITS == 4) mma_acc<A>(a.XS[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].z, xv[mt].w);
+      if constexpr (BITS == 4) {
+        if constexpr (FRESH) mma_zero<A>(a.XT[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].z, xv[mt].w);
+        else mma_acc<A>(a.XT[mt], kOnes, kOnes, kOnes, kOnes, xv[mt].z, xv[mt].w);
+      }
     }
   }
   if constexpr (BITS == 4 || F::NIB8) {
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
           const int c = 2 * tl + (i >> 1);
           float G = qa.P[mt][tl][i];
           if constexpr (HAS_Q) G = fmaf(qa.Q[mt][tl][i], F::QSCALE, G);
-          const float xsum_m = MT > 1 ? qa.XS[mt][i & 1] : X[mt][i & 1];
+          const float xsum_m = MT > 1 ? (BITS == 4 ? qa.XS[mt][i & 1] + qa.XT[mt][i & 1] : qa.XS[mt][i & 1]) : X[mt][i & 1];
           acc[mt][tl][i] = fmaf(sa[c], G, fmaf(sb[c], xsum_m, acc[mt][tl][i]));
         }
   };
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(MT == 1 ? 32 * (kStreamMaxWarps + 1) : 32 * 15
         qa.P[mt][0][k] = qa.P[mt][1][k] = 0.f;
         if constexpr (HAS_Q) qa.Q[mt][0][k] = qa.Q[mt][1][k] = 0.f;
         X[mt][k & 1] = 0.f;
-        if constexpr (MT > 1) qa.XS[mt][k] = 0.f;
+        if constexpr (MT > 1) qa.XS[mt][k] = qa.XT[mt][k] = 0.f;
       }
   };
   auto add_xsum = [&](int entry) {
